@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by executing the REFERENCE'S OWN source files.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It puts `oracle/chainer_shim` (torch-CPU stand-in for the un-installable
+chainer==4.0.0b1, see oracle/chainer_shim/README.md) and `/root/reference` on
+sys.path, imports the unmodified `models.base_model`, `models.transform` and
+`models.spational_transformer_sampler_interp`, replaces only the two CNNs
+(out of scope; `disp_net` / `pose_net` attributes) with stubs that return the
+seeded synthetic predictions, and records inputs, the five reported losses and
+the gradients w.r.t. disparities, poses and explainability logits.
+
+The fixtures travel with the repo; nothing at test time reads /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('SFM_REFERENCE', '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'chainer_shim'))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+import chainer                                                    # the shim
+from chainer import Variable
+import models.transform as ref_transform                          # reference code, unmodified
+import models.base_model as ref_base_model
+import models.spational_transformer_sampler_interp as ref_interp
+from sfm_learner_chainer_b200.synthetic import make_snippets
+
+assert chainer.__version__.endswith('shim')
+
+CASES = [
+    # name, B, S, H, W, seed, harsh, flags (experiments/sfm_learner_v1*.yml architecture blocks)
+    ('v1',        2, 2, 32, 104, 0, False, dict(smooth_reg=0.0, exp_reg=0.0, seq_len=3)),
+    ('v1_ssim',   2, 2, 32, 104, 1, False, dict(smooth_reg=0.1, exp_reg=0, seq_len=3, ssim_rate=0.15)),
+    ('v1_odom',   2, 4, 32, 104, 2, False, dict(smooth_reg=0.1, exp_reg=0.2, seq_len=5)),
+    ('v1_ssim_harsh', 1, 2, 48, 160, 3, True, dict(smooth_reg=0.1, exp_reg=0, seq_len=3, ssim_rate=0.15)),
+    ('v1_odom_harsh', 1, 4, 48, 160, 4, True, dict(smooth_reg=0.1, exp_reg=0.2, seq_len=5)),
+]
+
+
+def reset_reference_caches():
+    ref_transform.filler = None        # transform.py:62 (keyed on N only)
+    ref_transform.meshgrid = None      # transform.py:135 (keyed on H*W only)
+
+
+def run_model(data, flags, dtype):
+    reset_reference_caches()
+    chainer.clear_reports()
+    model = ref_base_model.SFMLearner(flags, {'download': None, 'path': None})
+    cast = lambda a: np.ascontiguousarray(a.astype(dtype))
+    disps = [Variable(cast(d)) for d in data['disps']]
+    S = data['src'].shape[1]
+    poses = [Variable(cast(data['poses'][:, i])) for i in range(S)]
+    masks = [Variable(cast(l)) for l in data['logits']]
+    model.disp_net = lambda tgt: disps
+    model.pose_net = lambda tgt, src, do_exp=True: (tuple(poses), masks if do_exp else None)
+    K = cast(data['intrinsics'])
+    loss = model(cast(data['tgt']), cast(data['src']), K, K)
+    loss.backward()
+    rep = chainer.get_reports()
+    out = {}
+    for k in ('total_loss', 'pixel_loss', 'smooth_loss', 'exp_loss', 'ssim_loss'):
+        v = rep[k]
+        out[k] = float(v.data) if isinstance(v, Variable) else float(v)
+    out['gdisp'] = [d.grad for d in disps]
+    out['gpose'] = np.stack([p.grad for p in poses], axis=1)
+    do_exp = flags['exp_reg'] is not None and flags['exp_reg'] > 0
+    out['glogits'] = [m.grad for m in masks] if do_exp else None
+    return out
+
+
+def run_warp(data, dtype, scale=0, i=0):
+    """projective_inverse_warp (transform.py:156) + its stages at one scale."""
+    reset_reference_caches()
+    cast = lambda a: np.ascontiguousarray(a.astype(dtype))
+    B, S, _, H, W = data['src'].shape
+    h, w = H >> scale, W >> scale
+    stacked = cast(data['src']).reshape(B, 3 * S, H, W)
+    img = chainer.functions.resize_images(stacked, (h, w)).data[:, 3 * i:3 * i + 3]
+    depth = 1.0 / cast(data['disps'][scale])
+    depth3 = np.broadcast_to(depth.reshape(B, 1, -1), (B, 3, h * w))
+    K = cast(data['intrinsics'][:, scale])
+    pose = cast(data['poses'][:, i])
+    P = ref_transform.projective_inverse_warp(img, Variable(np.ascontiguousarray(depth3)), Variable(pose), K)
+    reset_reference_caches()
+    proj = ref_transform.proj_tgt_to_src(Variable(pose), K, B)
+    pix = ref_transform.generate_2dmeshgrid(h, w, B)
+    cam = ref_transform.pixel2cam(Variable(np.ascontiguousarray(depth3)), pix, K, img.shape)
+    grid = ref_transform.cam2pixel(cam, proj, img.shape)
+    return dict(img=img, P=P.data, proj=proj.data, grid=grid.data)
+
+
+def run_interp(seed):
+    """SpatialTransformerSamplerInterp forward/backward (pixel-unit grid, clamped)."""
+    rs = np.random.RandomState(seed)
+    B, C, H, W, oh, ow = 2, 3, 12, 20, 9, 17
+    x = rs.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    grid = np.stack([rs.uniform(-3, W + 2, (B, oh, ow)), rs.uniform(-3, H + 2, (B, oh, ow))], 1).astype(np.float32)
+    gy = rs.uniform(-1, 1, (B, C, oh, ow)).astype(np.float32)
+    xv, gv = Variable(x), Variable(grid)
+    y = ref_interp.spatial_transformer_sampler_interp(xv, gv)
+    y._t.backward(__import__('torch').from_numpy(gy))
+    return dict(x=x, grid=grid, gy=gy, y=y.data, gx=xv.grad, ggrid=gv.grad)
+
+
+def main():
+    for name, B, S, H, W, seed, harsh, flags in CASES:
+        data = make_snippets(B, S, H, W, seed=seed, harsh=harsh, rough_disp=(seed % 2 == 1))
+        blob = dict(tgt=data['tgt'], src=data['src'], intrinsics=data['intrinsics'], poses=data['poses'],
+                    flags=np.array([flags['smooth_reg'], flags['exp_reg'] or 0.0, flags.get('ssim_rate', 0.0)]))
+        for s in range(4):
+            blob['disp%d' % s] = data['disps'][s]
+            blob['logits%d' % s] = data['logits'][s]
+        for tag, dtype in (('f64', np.float64), ('f32', np.float32)):
+            out = run_model(data, flags, dtype)
+            blob['losses_' + tag] = np.array([out[k] for k in ('total_loss', 'pixel_loss', 'smooth_loss',
+                                                               'exp_loss', 'ssim_loss')], np.float64)
+            blob['gpose_' + tag] = out['gpose']
+            for s in range(4):
+                blob['gdisp%d_%s' % (s, tag)] = out['gdisp'][s]
+                if out['glogits'] is not None:
+                    blob['glogits%d_%s' % (s, tag)] = out['glogits'][s]
+            print(name, tag, blob['losses_' + tag])
+        for sc in (0, 2):
+            wout = run_warp(data, np.float64, scale=sc, i=S - 1)
+            blob['warp_s%d_P_f64' % sc] = wout['P']
+            blob['warp_s%d_grid_f64' % sc] = wout['grid']
+            blob['warp_s%d_proj_f64' % sc] = wout['proj']
+            blob['warp_s%d_img_f64' % sc] = wout['img']
+        np.savez_compressed(os.path.join(HERE, 'loss_%s.npz' % name), **blob)
+    np.savez_compressed(os.path.join(HERE, 'interp_sampler.npz'), **run_interp(7))
+    print('golden fixtures written to', HERE)
+
+
+if __name__ == '__main__':
+    main()
