@@ -1,0 +1,187 @@
+/*
+ * sfmloss.h -- C ABI of libsfmloss.so: the SfM-Learner view-synthesis loss path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of pfnet/sfm-learner-chainer.  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference repo root).
+ * The reference-side binding (ctypes + Chainer FunctionNode) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / cupy types.
+ *  - All tensors are float32, C-contiguous, resident on the CURRENT CUDA device; the caller owns
+ *    every buffer (CuPy memory pool, torch allocator, cudaMalloc ...).  The library never frees or
+ *    retains caller pointers after a call returns, except inside an SfmHostCtx it created itself.
+ *  - Every call is asynchronous on `stream` (0 = legacy default stream), performs no host
+ *    synchronisation and no D2H copy, and is capturable in a CUDA graph (the *_host entry point is
+ *    the exception: it copies and synchronises by contract).
+ *  - Return value: 0 = OK, < 0 = SFM_E_* argument error, > 0 = cudaError_t.  The message of the
+ *    last failure on the calling thread is available from sfm_last_error().
+ *  - There is NO CPU fallback: without a CUDA device the compute entry points return an error.
+ */
+#ifndef SFMLOSS_H_
+#define SFMLOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_VERSION 100           /* major*100 + minor */
+#define SFM_MAX_SCALES 4          /* base_model.py:66 (len(pred_depthes) == 4) */
+#define SFM_MAX_SOURCES 8         /* seq_len-1; shipped configs use 2 and 4 */
+
+/* error codes */
+#define SFM_OK 0
+#define SFM_E_INVALID_DESC (-1)
+#define SFM_E_INVALID_SHAPE (-2)
+#define SFM_E_NULL_POINTER (-3)
+#define SFM_E_UNSUPPORTED (-4)
+#define SFM_E_NO_DEVICE (-5)
+
+/* SfmDesc.flags */
+#define SFM_FLAG_TABLES_PROVIDED 0x1u /* caller supplies proj/kinv tables (bit-exact tests; the reference
+                                         itself builds P on the host, transform.py:76-90) */
+#define SFM_FLAG_REUSE_PYRAMID 0x2u   /* workspace already holds this batch's image pyramid */
+#define SFM_FLAG_NO_TMA 0x4u          /* force the plain-load tile path (debug / A-B measurement) */
+
+/*
+ * Problem descriptor.  Mirrors the reference's model flags (base_model.py:37-39:
+ * smooth_reg, exp_reg, ssim_rate; experiments/sfm_learner_v1*.yml `architecture:` blocks) and the
+ * tensor shapes SFMLearner.__call__ receives (base_model.py:48-58).
+ * A flag <= 0 disables its term exactly like the Python truthiness tests at base_model.py:75,86,103,112;
+ * the explainability branch and SSIM are mutually exclusive as in the reference (:103-115).
+ */
+typedef struct SfmDesc {
+  int32_t B;         /* snippets held by this process                                  */
+  int32_t S;         /* source views per snippet (seq_len - 1)                         */
+  int32_t H, W;      /* full resolution; scale s is (H >> s, W >> s)                   */
+  int32_t n_scales;  /* 1..SFM_MAX_SCALES                                              */
+  int32_t B_global;  /* batch every F.mean divides by (0 = B); > B when snippet-sharded */
+  float smooth_reg;
+  float exp_reg;
+  float ssim_rate;
+  uint32_t flags;
+} SfmDesc;
+
+/* Inputs of one loss evaluation.  Shapes as produced by the reference's nets and dataset:
+ *   tgt        (B,3,H,W)            base_model.py:48
+ *   src        (B,S,3,H,W)          base_model.py:57-58 (== stacked (B,3S,H,W))
+ *   intrinsics (B,n_scales,3,3)     datasets/kitti/kitti_raw_transformed.py:76-93
+ *   disps[s]   (B,1,H>>s,W>>s)      models/disp_net.py:124   (disparity, NOT depth)
+ *   poses      (B,S,6)              models/pose_net.py:52-54 (rx,ry,rz,tx,ty,tz per source)
+ *   logits[s]  (B,S,H>>s,W>>s)      models/pose_net.py:56-67; may be NULL when exp_reg <= 0
+ *   proj       (B,S,n_scales,3,4)   only with SFM_FLAG_TABLES_PROVIDED: K4.T rows 0..2 (transform.py:86-88)
+ *   kinv       (B,n_scales,3,3)     only with SFM_FLAG_TABLES_PROVIDED: inverse intrinsics (transform.py:105)
+ */
+typedef struct SfmInputs {
+  const float* tgt;
+  const float* src;
+  const float* intrinsics;
+  const float* disps[SFM_MAX_SCALES];
+  const float* poses;
+  const float* logits[SFM_MAX_SCALES];
+  const float* proj;
+  const float* kinv;
+} SfmInputs;
+
+/* Gradients w.r.t. the network outputs (base_model.py:59-63 are the producers).  Same shapes as the
+ * corresponding inputs.  glogits may be NULL when exp_reg <= 0. */
+typedef struct SfmGrads {
+  float* gdisps[SFM_MAX_SCALES];
+  float* gposes;
+  float* glogits[SFM_MAX_SCALES];
+} SfmGrads;
+
+/* Optional per-(scale, source) dumps of the warp for stage-level parity tests (may be NULL):
+ *   P[s]   (B,S,3,h,w) f32  warped image            (transform.py:189)
+ *   u0[s]  (B,S,h,w)   i32  floor(u), v0 likewise   (integer work: must be bit-exact)
+ *   inb[s] (B,S,h,w)   u8   strict in-bounds flag   (transform.py:128-131)               */
+typedef struct SfmDebug {
+  float* P[SFM_MAX_SCALES];
+  int32_t* u0[SFM_MAX_SCALES];
+  int32_t* v0[SFM_MAX_SCALES];
+  uint8_t* inb[SFM_MAX_SCALES];
+} SfmDebug;
+
+int sfm_version(void);
+const char* sfm_last_error(void);
+
+/* Bytes of device scratch a call needs (image pyramid in NHWC4, projection tables, fp64 reduction
+ * cells).  The caller allocates it (any 256-byte aligned device pointer) and passes it to every call
+ * with the same descriptor. */
+size_t sfm_workspace_bytes(const SfmDesc* desc);
+
+/* losses_out: device float[5] = total, pixel, smooth, exp, ssim  (chainer.report keys,
+ * base_model.py:119-123).  Under snippet sharding they are this shard's partial sums; add across
+ * ranks (one allreduce of 5 floats). */
+
+/* Forward only.  Replaces SFMLearner.__call__'s loss loop, base_model.py:64-118
+ * (F.resize_images :71-72, projective_inverse_warp transform.py:156-193, compute_smooth_loss :169-185,
+ * compute_exp_reg_loss :157-167, compute_ssim :126-142). */
+int sfm_loss_forward(const SfmDesc* desc, const SfmInputs* in, float* losses_out, const SfmDebug* debug,
+                     void* workspace, void* stream);
+
+/* Backward only (recomputes the forward).  Replaces loss.backward() through the graph recorded by
+ * base_model.py:64-118.  gy: device float* holding dL/dloss, or NULL for 1. */
+int sfm_loss_backward(const SfmDesc* desc, const SfmInputs* in, const float* gy, const SfmGrads* grads,
+                      void* workspace, void* stream);
+
+/* Fused single pass: losses and gradients (for upstream gradient 1) in one sweep.  This is what the
+ * Chainer adapter calls from forward(); its backward() only rescales (sfm_scale_grads). */
+int sfm_loss_forward_backward(const SfmDesc* desc, const SfmInputs* in, float* losses_out,
+                              const SfmGrads* grads, void* workspace, void* stream);
+
+/* grads *= *gy (device scalar).  No-op on the device when *gy == 1. */
+int sfm_scale_grads(const SfmDesc* desc, const float* gy, const SfmGrads* grads, void* stream);
+
+/* Image pyramid only (F.resize_images from full resolution, base_model.py:70-72) into the workspace;
+ * sfm_pyramid_export copies one level back out as NCHW for tests:
+ * tgt_out (B,3,h,w), src_out (B,S,3,h,w). */
+int sfm_pyramid(const SfmDesc* desc, const float* tgt, const float* src, void* workspace, void* stream);
+int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, int scale, float* tgt_out, float* src_out,
+                       void* stream);
+
+/* Projection tables on the device: proj_out (B,S,n_scales,3,4), kinv_out (B,n_scales,3,3).
+ * Replaces proj_tgt_to_src / pose_vec2mat / euler2mat (transform.py:11-91) and F.batch_inv(K) (:105),
+ * including the five blocking host<->device copies per (scale, source) of models/utils.py:33-84. */
+int sfm_build_tables(const SfmDesc* desc, const float* poses, const float* intrinsics, float* proj_out,
+                     float* kinv_out, void* stream);
+
+/* Stage API: projective_inverse_warp(imgs, depthes, poses, K) of transform.py:156-165 on N images of
+ * one resolution.  imgs (N,3,h,w) NCHW, depth (N,h*w) [the reference passes it broadcast to 3 rows],
+ * poses (N,6), K (N,3,3); proj (N,3,4) / kinv (N,3,3) optional overrides (NULL = built on device).
+ * Outputs: out (N,3,h,w); optional u0,v0 (N,h,w) int32 and inb (N,h,w) uint8. */
+int sfm_warp_forward(int N, int h, int w, const float* imgs, const float* depth, const float* poses,
+                     const float* K, const float* proj, const float* kinv, float* out, int32_t* u0,
+                     int32_t* v0, uint8_t* inb, void* stream);
+/* Backward of the above for upstream gy (N,3,h,w): gdepth (N,h*w), gposes (N,6), optional gimgs
+ * (N,3,h,w; the reference discards it, base_model.py:71-72 `.data`).  scratch: device buffer of
+ * sfm_warp_backward_scratch_bytes(N) bytes. */
+size_t sfm_warp_backward_scratch_bytes(int N);
+int sfm_warp_backward(int N, int h, int w, const float* imgs, const float* depth, const float* poses,
+                      const float* K, const float* gy, float* gdepth, float* gposes, float* gimgs,
+                      void* scratch, void* stream);
+
+/* SpatialTransformerSamplerInterp (models/spational_transformer_sampler_interp.py:9-159, the repo-local
+ * sampler the live path leaves commented out, transform.py:190-191): grid in PIXEL units, indices
+ * clamped to the image.  x (B,C,H,W), grid (B,2,oH,oW) -> y (B,C,oH,oW);  backward returns ggrid
+ * (B,2,oH,oW) and gx = zeros (:148). */
+int sfm_sampler_interp_forward(int B, int C, int H, int W, int oH, int oW, const float* x, const float* grid,
+                               float* y, void* stream);
+int sfm_sampler_interp_backward(int B, int C, int H, int W, int oH, int oW, const float* x, const float* grid,
+                                const float* gy, float* gx, float* ggrid, void* stream);
+
+/* Host-buffer convenience path (what a CPU-resident caller, e.g. a Chainer numpy run or the end-to-end
+ * benchmark, uses): owns device buffers, copies inputs H2D, runs sfm_loss_forward_backward, copies
+ * losses and gradients D2H and synchronises.  All pointers in `in`, `grads` and `losses_out` are HOST
+ * pointers here (pinned memory makes the copies asynchronous). */
+typedef struct SfmHostCtx SfmHostCtx;
+int sfm_host_ctx_create(const SfmDesc* desc, SfmHostCtx** ctx_out);
+int sfm_host_ctx_destroy(SfmHostCtx* ctx);
+int sfm_loss_step_host(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, const SfmGrads* grads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFMLOSS_H_ */

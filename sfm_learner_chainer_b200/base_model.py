@@ -1,0 +1,60 @@
+"""SFMLearner with the reference's call surface (models/base_model.py:28-124) whose loss loop runs in
+the fused B200 kernels.  The two CNNs are whatever the caller plugs in (Chainer links in the
+reference, torch modules in this image); they are outside the hot path and untouched."""
+from . import device as D
+from .functions import ViewSynthesisLoss
+from .lib import LOSS_KEYS
+
+
+def parse_dict(dic, key, value=None):
+    return value if dic is None or key not in dic else dic[key]
+
+
+class SFMLearner(object):
+    """SFMLearner(config, pretrained_model=None, disp_net=..., pose_net=...)
+
+    config keys as in experiments/*.yml `architecture:` -- seq_len, smooth_reg, exp_reg, ssim_rate
+    (base_model.py:32-39).  __call__(tgt_img, src_imgs, intrinsics, inv_intrinsics) returns the total
+    loss and reports total/pixel/smooth/exp/ssim_loss (base_model.py:119-123) through `reporter`
+    (default: stored in `self.last_report`; pass `chainer.report`-style callable to forward them).
+    """
+
+    def __init__(self, config, pretrained_model=None, disp_net=None, pose_net=None, reporter=None,
+                 B_global=None):
+        self.n_sources = config['seq_len'] - 1
+        self.smooth_reg = config['smooth_reg']
+        self.exp_reg = config['exp_reg']
+        self.ssim_rate = parse_dict(config, 'ssim_rate', 0.0)
+        self.disp_net = disp_net
+        self.pose_net = pose_net
+        self.reporter = reporter
+        self.last_report = {}
+        self.last_grads = None
+        self.loss_op = ViewSynthesisLoss(self.smooth_reg, self.exp_reg, self.ssim_rate, B_global=B_global)
+
+    def __call__(self, tgt_img, src_imgs, intrinsics, inv_intrinsics=None):
+        batchsize, n_sources, _, H, W = src_imgs.shape
+        stacked_src_imgs = src_imgs.reshape(batchsize, -1, H, W)
+        pred_disps = self.disp_net(tgt_img)
+        do_exp = self.exp_reg is not None and self.exp_reg > 0
+        pred_poses, pred_maskes = self.pose_net(tgt_img, stacked_src_imgs, do_exp=do_exp)
+        first = pred_disps[0]
+        if D.is_torch(first) and getattr(first, 'requires_grad', False):
+            from .torch_adapter import view_synthesis_loss
+            total, losses = view_synthesis_loss(self.loss_op, tgt_img, src_imgs, intrinsics, pred_disps,
+                                                pred_poses, pred_maskes)
+        elif type(first).__module__.startswith('chainer'):
+            from .chainer_adapter import view_synthesis_loss
+            total, losses = view_synthesis_loss(self.loss_op, tgt_img, src_imgs, intrinsics, pred_disps,
+                                                pred_poses, pred_maskes)
+        else:
+            if isinstance(pred_poses, (tuple, list)):
+                raise TypeError('array-level call needs pred_poses as one (B,S,6) device array')
+            losses, self.last_grads = self.loss_op.forward_backward(tgt_img, src_imgs, intrinsics, pred_disps,
+                                                                    pred_poses, pred_maskes)
+            total = losses[0]
+        self.last_report = dict(zip(LOSS_KEYS, (losses[i] for i in range(5))))
+        if self.reporter is not None:
+            for k in LOSS_KEYS:
+                self.reporter({k: self.last_report[k]}, self)
+        return total

@@ -1,0 +1,396 @@
+// api.cu -- extern "C" entry points of libsfmloss.so (see include/sfmloss.h for the contract and the
+// reference interfaces each one replaces).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void sfm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* sfm_last_error(void) { return g_err; }
+extern "C" int sfm_version(void) { return SFM_VERSION; }
+
+int sfm_validate_desc(const SfmDesc* d) {
+  if (!d) { sfm_set_error("SfmDesc is NULL"); return SFM_E_NULL_POINTER; }
+  if (d->B < 1 || d->S < 1 || d->S > SFM_MAX_SOURCES || d->n_scales < 1 || d->n_scales > SFM_MAX_SCALES) {
+    sfm_set_error("invalid SfmDesc: B=%d S=%d (1..%d) n_scales=%d (1..%d)", d->B, d->S, SFM_MAX_SOURCES, d->n_scales, SFM_MAX_SCALES);
+    return SFM_E_INVALID_DESC;
+  }
+  if (d->B_global != 0 && d->B_global < d->B) {
+    sfm_set_error("invalid SfmDesc: B_global=%d < B=%d", d->B_global, d->B);
+    return SFM_E_INVALID_DESC;
+  }
+  const int hs = d->H >> (d->n_scales - 1), ws = d->W >> (d->n_scales - 1);
+  if (d->H < 2 || d->W < 2 || hs < 3 || ws < 3) {
+    // resize_images needs >= 2 input rows/cols; the smoothness means need (h-2)*(w-2) > 0 at every scale
+    sfm_set_error("invalid shape: H=%d W=%d give %dx%d at the coarsest of %d scales (need >= 3x3)", d->H, d->W, hs, ws, d->n_scales);
+    return SFM_E_INVALID_SHAPE;
+  }
+  if ((long long)d->B * (1 + d->S) * d->H * d->W >= (1ll << 31)) {
+    sfm_set_error("invalid shape: B*(1+S)*H*W exceeds 2^31 pixels");
+    return SFM_E_INVALID_SHAPE;
+  }
+  if (!(d->smooth_reg == d->smooth_reg) || !(d->exp_reg == d->exp_reg) || !(d->ssim_rate == d->ssim_rate)) {
+    sfm_set_error("invalid SfmDesc: NaN loss weight");
+    return SFM_E_INVALID_DESC;
+  }
+  return 0;
+}
+
+extern "C" size_t sfm_workspace_bytes(const SfmDesc* desc) {
+  if (sfm_validate_desc(desc) != 0) return 0;
+  SfmWsLayout L;
+  sfm_ws_layout(desc, &L);
+  return L.total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// common driver
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Modes {
+  bool use_exp, use_ssim, use_smooth;
+};
+
+// Python truthiness of the reference's flags (base_model.py:75,86,103,112): 0 / 0.0 disable a term;
+// SSIM sits in the else-branch of the explainability test (:103-115).
+Modes modes_of(const SfmDesc* d) {
+  Modes m;
+  m.use_exp = d->exp_reg != 0.f;
+  m.use_ssim = !m.use_exp && d->ssim_rate != 0.f;
+  m.use_smooth = d->smooth_reg != 0.f;
+  return m;
+}
+
+int check_inputs(const SfmDesc* d, const SfmInputs* in, bool need_images) {
+  if (!in) { sfm_set_error("SfmInputs is NULL"); return SFM_E_NULL_POINTER; }
+  const Modes m = modes_of(d);
+  if (need_images && (!in->tgt || !in->src)) { sfm_set_error("tgt/src image pointer is NULL"); return SFM_E_NULL_POINTER; }
+  if (!in->intrinsics || !in->poses) { sfm_set_error("intrinsics/poses pointer is NULL"); return SFM_E_NULL_POINTER; }
+  for (int s = 0; s < d->n_scales; ++s) {
+    if (!in->disps[s]) { sfm_set_error("disps[%d] is NULL", s); return SFM_E_NULL_POINTER; }
+    if (m.use_exp && !in->logits[s]) { sfm_set_error("exp_reg > 0 but logits[%d] is NULL", s); return SFM_E_NULL_POINTER; }
+  }
+  if ((d->flags & SFM_FLAG_TABLES_PROVIDED) && (!in->proj || !in->kinv)) {
+    sfm_set_error("SFM_FLAG_TABLES_PROVIDED set but proj/kinv is NULL");
+    return SFM_E_NULL_POINTER;
+  }
+  return 0;
+}
+
+int check_grads(const SfmDesc* d, const SfmGrads* g) {
+  if (!g) { sfm_set_error("SfmGrads is NULL"); return SFM_E_NULL_POINTER; }
+  const Modes m = modes_of(d);
+  if (!g->gposes) { sfm_set_error("gposes is NULL"); return SFM_E_NULL_POINTER; }
+  for (int s = 0; s < d->n_scales; ++s) {
+    if (!g->gdisps[s]) { sfm_set_error("gdisps[%d] is NULL", s); return SFM_E_NULL_POINTER; }
+    if (m.use_exp && !g->glogits[s]) { sfm_set_error("exp_reg > 0 but glogits[%d] is NULL", s); return SFM_E_NULL_POINTER; }
+  }
+  return 0;
+}
+
+int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyramid, cudaStream_t st) {
+  SfmWsLayout L;
+  sfm_ws_layout(d, &L);
+  char* ws = (char*)workspace;
+  SfmPrepParams p{};
+  p.B = d->B; p.S = d->S; p.H = d->H; p.W = d->W; p.ns = d->n_scales;
+  p.do_pyramid = do_pyramid ? 1 : 0;
+  p.build_tables = (d->flags & SFM_FLAG_TABLES_PROVIDED) ? 0 : 1;
+  p.tgt = in->tgt; p.src = in->src; p.intrinsics = in->intrinsics; p.poses = in->poses;
+  for (int s = 0; s < d->n_scales; ++s) {
+    p.tgt_pyr[s] = (float4*)(ws + L.off_tgt[s]);
+    p.src_pyr[s] = (float4*)(ws + L.off_src[s]);
+  }
+  p.proj_out = (float*)(ws + L.off_proj);
+  p.kinv_out = (float*)(ws + L.off_kinv);
+  p.acc = (double*)(ws + L.off_acc);
+  p.n_acc = (int)L.acc_doubles;
+  p.counter = (unsigned*)(ws + L.off_counter);
+  return sfm_launch_prep(p, st);
+}
+
+int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const SfmGrads* grads, const float* gy,
+             const SfmDebug* dbg, void* workspace, cudaStream_t st) {
+  int rc = sfm_validate_desc(d);
+  if (rc) return rc;
+  const bool reuse = (d->flags & SFM_FLAG_REUSE_PYRAMID) != 0;
+  rc = check_inputs(d, in, !reuse);
+  if (rc) return rc;
+  if (grads && (rc = check_grads(d, grads))) return rc;
+  if (!workspace) { sfm_set_error("workspace is NULL"); return SFM_E_NULL_POINTER; }
+  if (((uintptr_t)workspace & 255) != 0) { sfm_set_error("workspace must be 256-byte aligned"); return SFM_E_INVALID_DESC; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    sfm_set_error("no CUDA device: libsfmloss has no CPU fallback");
+    return SFM_E_NO_DEVICE;
+  }
+  rc = run_prep(d, in, workspace, !reuse, st);
+  if (rc) return rc;
+
+  const Modes m = modes_of(d);
+  SfmWsLayout L;
+  sfm_ws_layout(d, &L);
+  char* ws = (char*)workspace;
+  SfmFusedParams p{};
+  p.B = d->B; p.S = d->S; p.ns = d->n_scales;
+  const double Bg = (double)(d->B_global > 0 ? d->B_global : d->B);
+  for (int s = 0; s < d->n_scales; ++s) {
+    const int h = d->H >> s, w = d->W >> s;
+    p.h[s] = h; p.w[s] = w;
+    p.tgt_pyr[s] = (const float4*)(ws + L.off_tgt[s]);
+    p.src_pyr[s] = (const float4*)(ws + L.off_src[s]);
+    p.disp[s] = in->disps[s];
+    p.logits[s] = m.use_exp ? in->logits[s] : nullptr;
+    p.gdisp[s] = grads ? grads->gdisps[s] : nullptr;
+    p.glogits[s] = (grads && m.use_exp) ? grads->glogits[s] : nullptr;
+    p.inv_n3[s] = (float)(1.0 / (Bg * 3.0 * h * w));
+    p.inv_n1[s] = (float)(1.0 / (Bg * h * w));
+    const double wgt = (double)d->smooth_reg / (double)(1 << s);
+    p.sm_dx2[s] = (float)(wgt / (Bg * h * (w - 2)));
+    p.sm_mix[s] = (float)(wgt / (Bg * (h - 1) * (w - 1)));
+    p.sm_dy2[s] = (float)(wgt / (Bg * (h - 2) * w));
+    if (dbg) {
+      p.dbg_P[s] = dbg->P[s]; p.dbg_u0[s] = dbg->u0[s]; p.dbg_v0[s] = dbg->v0[s]; p.dbg_inb[s] = dbg->inb[s];
+    }
+  }
+  const bool tables = (d->flags & SFM_FLAG_TABLES_PROVIDED) != 0;
+  p.proj = tables ? in->proj : (const float*)(ws + L.off_proj);
+  p.kinv = tables ? in->kinv : (const float*)(ws + L.off_kinv);
+  p.intrinsics = in->intrinsics;
+  p.poses = in->poses;
+  p.gy = gy;
+  p.acc = (double*)(ws + L.off_acc);
+  p.counter = (unsigned*)(ws + L.off_counter);
+  p.losses_out = losses_out;
+  p.gposes = grads ? grads->gposes : nullptr;
+  p.smooth_reg = d->smooth_reg;
+  p.exp_reg = m.use_exp ? d->exp_reg : 0.f;
+  p.ssim_rate = d->ssim_rate;     // enters `total` even when the SSIM term itself is skipped (base_model.py:117)
+  p.use_smooth = m.use_smooth ? 1 : 0;
+  int mode = 0;
+  if (m.use_exp) mode |= SFM_MODE_EXP;
+  if (m.use_ssim) mode |= SFM_MODE_SSIM;
+  if (grads) mode |= SFM_MODE_GRAD;
+  if (dbg) mode |= SFM_MODE_DEBUG;
+  return sfm_launch_fused(p, mode, st);
+}
+
+}  // namespace
+
+extern "C" int sfm_loss_forward(const SfmDesc* desc, const SfmInputs* in, float* losses_out, const SfmDebug* debug,
+                                void* workspace, void* stream) {
+  if (!losses_out) { sfm_set_error("losses_out is NULL"); return SFM_E_NULL_POINTER; }
+  return run_loss(desc, in, losses_out, nullptr, nullptr, debug, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_loss_backward(const SfmDesc* desc, const SfmInputs* in, const float* gy, const SfmGrads* grads,
+                                 void* workspace, void* stream) {
+  if (!grads) { sfm_set_error("grads is NULL"); return SFM_E_NULL_POINTER; }
+  return run_loss(desc, in, nullptr, grads, gy, nullptr, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_loss_forward_backward(const SfmDesc* desc, const SfmInputs* in, float* losses_out,
+                                         const SfmGrads* grads, void* workspace, void* stream) {
+  if (!losses_out) { sfm_set_error("losses_out is NULL"); return SFM_E_NULL_POINTER; }
+  if (!grads) { sfm_set_error("grads is NULL"); return SFM_E_NULL_POINTER; }
+  return run_loss(desc, in, losses_out, grads, nullptr, nullptr, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_scale_grads(const SfmDesc* desc, const float* gy, const SfmGrads* grads, void* stream) {
+  int rc = sfm_validate_desc(desc);
+  if (rc) return rc;
+  if (!gy) { sfm_set_error("gy is NULL"); return SFM_E_NULL_POINTER; }
+  if ((rc = check_grads(desc, grads))) return rc;
+  const Modes m = modes_of(desc);
+  float* ptrs[2 * SFM_MAX_SCALES + 1];
+  long long counts[2 * SFM_MAX_SCALES + 1];
+  int n = 0;
+  for (int s = 0; s < desc->n_scales; ++s) {
+    const long long hw = (long long)(desc->H >> s) * (desc->W >> s);
+    ptrs[n] = grads->gdisps[s]; counts[n++] = desc->B * hw;
+    if (m.use_exp) { ptrs[n] = grads->glogits[s]; counts[n++] = (long long)desc->B * desc->S * hw; }
+  }
+  ptrs[n] = grads->gposes; counts[n++] = (long long)desc->B * desc->S * 6;
+  return sfm_launch_scale(ptrs, counts, n, gy, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_pyramid(const SfmDesc* desc, const float* tgt, const float* src, void* workspace, void* stream) {
+  int rc = sfm_validate_desc(desc);
+  if (rc) return rc;
+  if (!tgt || !src || !workspace) { sfm_set_error("sfm_pyramid: null pointer"); return SFM_E_NULL_POINTER; }
+  SfmWsLayout L;
+  sfm_ws_layout(desc, &L);
+  char* ws = (char*)workspace;
+  SfmPrepParams p{};
+  p.B = desc->B; p.S = desc->S; p.H = desc->H; p.W = desc->W; p.ns = desc->n_scales;
+  p.do_pyramid = 1; p.build_tables = 0;
+  p.tgt = tgt; p.src = src;
+  for (int s = 0; s < desc->n_scales; ++s) {
+    p.tgt_pyr[s] = (float4*)(ws + L.off_tgt[s]);
+    p.src_pyr[s] = (float4*)(ws + L.off_src[s]);
+  }
+  p.acc = (double*)(ws + L.off_acc);
+  p.n_acc = 0;
+  p.counter = nullptr;
+  return sfm_launch_prep(p, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, int scale, float* tgt_out,
+                                  float* src_out, void* stream) {
+  int rc = sfm_validate_desc(desc);
+  if (rc) return rc;
+  if (scale < 0 || scale >= desc->n_scales) { sfm_set_error("sfm_pyramid_export: scale %d out of range", scale); return SFM_E_INVALID_DESC; }
+  if (!workspace) { sfm_set_error("sfm_pyramid_export: null workspace"); return SFM_E_NULL_POINTER; }
+  SfmWsLayout L;
+  sfm_ws_layout(desc, &L);
+  const char* ws = (const char*)workspace;
+  const int hw = (desc->H >> scale) * (desc->W >> scale);
+  if (tgt_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_tgt[scale]), tgt_out, desc->B, hw, (cudaStream_t)stream))) return rc;
+  if (src_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_src[scale]), src_out, (long long)desc->B * desc->S, hw, (cudaStream_t)stream))) return rc;
+  return 0;
+}
+
+extern "C" int sfm_build_tables(const SfmDesc* desc, const float* poses, const float* intrinsics, float* proj_out,
+                                float* kinv_out, void* stream) {
+  int rc = sfm_validate_desc(desc);
+  if (rc) return rc;
+  if (!poses || !intrinsics || !proj_out || !kinv_out) { sfm_set_error("sfm_build_tables: null pointer"); return SFM_E_NULL_POINTER; }
+  SfmPrepParams p{};
+  p.B = desc->B; p.S = desc->S; p.H = desc->H; p.W = desc->W; p.ns = desc->n_scales;
+  p.do_pyramid = 0; p.build_tables = 1;
+  p.intrinsics = intrinsics; p.poses = poses;
+  p.proj_out = proj_out; p.kinv_out = kinv_out;
+  p.acc = nullptr; p.n_acc = 0; p.counter = nullptr;
+  return sfm_launch_prep(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer path
+// ------------------------------------------------------------------------------------------------
+struct SfmHostCtx {
+  SfmDesc desc;
+  cudaStream_t stream;
+  void* workspace;
+  float *d_tgt, *d_src, *d_K, *d_poses, *d_losses, *d_gposes;
+  float* d_disp[SFM_MAX_SCALES];
+  float* d_logits[SFM_MAX_SCALES];
+  float* d_gdisp[SFM_MAX_SCALES];
+  float* d_glogits[SFM_MAX_SCALES];
+  std::vector<void*> allocs;
+};
+
+static int host_alloc(SfmHostCtx* c, void** p, size_t bytes) {
+  SFM_CUDA_CHECK(cudaMalloc(p, bytes));
+  c->allocs.push_back(*p);
+  return 0;
+}
+
+extern "C" int sfm_host_ctx_destroy(SfmHostCtx* ctx) {
+  if (!ctx) return 0;
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" int sfm_host_ctx_create(const SfmDesc* desc, SfmHostCtx** ctx_out) {
+  int rc = sfm_validate_desc(desc);
+  if (rc) return rc;
+  if (!ctx_out) { sfm_set_error("ctx_out is NULL"); return SFM_E_NULL_POINTER; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    sfm_set_error("no CUDA device: libsfmloss has no CPU fallback");
+    return SFM_E_NO_DEVICE;
+  }
+  SfmHostCtx* c = new (std::nothrow) SfmHostCtx();
+  if (!c) { sfm_set_error("out of host memory"); return SFM_E_INVALID_DESC; }
+  c->desc = *desc;
+  c->desc.flags &= ~(SFM_FLAG_TABLES_PROVIDED | SFM_FLAG_REUSE_PYRAMID);
+  const SfmDesc* d = &c->desc;
+  const Modes m = modes_of(d);
+  const size_t img = (size_t)d->H * d->W * 3 * sizeof(float);
+#define HA(ptr, bytes)                                                     \
+  if ((rc = host_alloc(c, (void**)&(ptr), (bytes)))) { sfm_host_ctx_destroy(c); return rc; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    sfm_set_error("cudaStreamCreate failed");
+    delete c;
+    return (int)cudaErrorUnknown;
+  }
+  HA(c->workspace, sfm_workspace_bytes(d));
+  HA(c->d_tgt, d->B * img);
+  HA(c->d_src, (size_t)d->B * d->S * img);
+  HA(c->d_K, (size_t)d->B * d->n_scales * 9 * sizeof(float));
+  HA(c->d_poses, (size_t)d->B * d->S * 6 * sizeof(float));
+  HA(c->d_gposes, (size_t)d->B * d->S * 6 * sizeof(float));
+  HA(c->d_losses, 8 * sizeof(float));
+  for (int s = 0; s < d->n_scales; ++s) {
+    const size_t hw = (size_t)(d->H >> s) * (d->W >> s) * sizeof(float);
+    HA(c->d_disp[s], d->B * hw);
+    HA(c->d_gdisp[s], d->B * hw);
+    if (m.use_exp) {
+      HA(c->d_logits[s], (size_t)d->B * d->S * hw);
+      HA(c->d_glogits[s], (size_t)d->B * d->S * hw);
+    }
+  }
+#undef HA
+  *ctx_out = c;
+  return 0;
+}
+
+extern "C" int sfm_loss_step_host(SfmHostCtx* c, const SfmInputs* in, float* losses_out, const SfmGrads* grads) {
+  if (!c || !in || !losses_out || !grads) { sfm_set_error("sfm_loss_step_host: null pointer"); return SFM_E_NULL_POINTER; }
+  const SfmDesc* d = &c->desc;
+  int rc = check_inputs(d, in, true);
+  if (rc) return rc;
+  if ((rc = check_grads(d, grads))) return rc;
+  const Modes m = modes_of(d);
+  cudaStream_t st = c->stream;
+  const size_t img = (size_t)d->H * d->W * 3 * sizeof(float);
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_tgt, in->tgt, d->B * img, cudaMemcpyHostToDevice, st));
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_src, in->src, (size_t)d->B * d->S * img, cudaMemcpyHostToDevice, st));
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_K, in->intrinsics, (size_t)d->B * d->n_scales * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_poses, in->poses, (size_t)d->B * d->S * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+  SfmInputs din{};
+  SfmGrads dg{};
+  din.tgt = c->d_tgt; din.src = c->d_src; din.intrinsics = c->d_K; din.poses = c->d_poses;
+  dg.gposes = c->d_gposes;
+  for (int s = 0; s < d->n_scales; ++s) {
+    const size_t hw = (size_t)(d->H >> s) * (d->W >> s) * sizeof(float);
+    SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_disp[s], in->disps[s], d->B * hw, cudaMemcpyHostToDevice, st));
+    din.disps[s] = c->d_disp[s];
+    dg.gdisps[s] = c->d_gdisp[s];
+    if (m.use_exp) {
+      SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_logits[s], in->logits[s], (size_t)d->B * d->S * hw, cudaMemcpyHostToDevice, st));
+      din.logits[s] = c->d_logits[s];
+      dg.glogits[s] = c->d_glogits[s];
+    }
+  }
+  rc = sfm_loss_forward_backward(d, &din, c->d_losses, &dg, c->workspace, st);
+  if (rc) return rc;
+  SFM_CUDA_CHECK(cudaMemcpyAsync(losses_out, c->d_losses, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SFM_CUDA_CHECK(cudaMemcpyAsync(grads->gposes, c->d_gposes, (size_t)d->B * d->S * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  for (int s = 0; s < d->n_scales; ++s) {
+    const size_t hw = (size_t)(d->H >> s) * (d->W >> s) * sizeof(float);
+    SFM_CUDA_CHECK(cudaMemcpyAsync(grads->gdisps[s], c->d_gdisp[s], d->B * hw, cudaMemcpyDeviceToHost, st));
+    if (m.use_exp)
+      SFM_CUDA_CHECK(cudaMemcpyAsync(grads->glogits[s], c->d_glogits[s], (size_t)d->B * d->S * hw, cudaMemcpyDeviceToHost, st));
+  }
+  SFM_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,71 @@
+// kernels.h -- kernel parameter blocks and launchers shared between the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sfmloss.h"
+
+struct SfmPrepParams {
+  int B, S, H, W, ns;
+  int do_pyramid;    // 0: only tables / accumulator reset
+  int build_tables;  // 0: caller supplied proj/kinv
+  const float* tgt;
+  const float* src;
+  const float* intrinsics;
+  const float* poses;
+  float4* tgt_pyr[SFM_MAX_SCALES];
+  float4* src_pyr[SFM_MAX_SCALES];
+  float* proj_out;
+  float* kinv_out;
+  double* acc;
+  int n_acc;
+  unsigned* counter;
+  // filled by the launcher
+  long long pix_begin[SFM_MAX_SCALES];
+  int n_pyr_blocks;
+};
+
+int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
+int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int hw, cudaStream_t stream);
+
+// Fused loss kernel parameters (one launch covers every scale, source and snippet).
+struct SfmFusedParams {
+  int B, S, ns;
+  int h[SFM_MAX_SCALES], w[SFM_MAX_SCALES];
+  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];
+  int tile_begin[SFM_MAX_SCALES + 1];
+  const float4* tgt_pyr[SFM_MAX_SCALES];
+  const float4* src_pyr[SFM_MAX_SCALES];
+  const float* disp[SFM_MAX_SCALES];
+  const float* logits[SFM_MAX_SCALES];
+  float* gdisp[SFM_MAX_SCALES];
+  float* glogits[SFM_MAX_SCALES];
+  const float* proj;        // [B][S][ns][12]
+  const float* kinv;        // [B][ns][9]
+  const float* intrinsics;  // [B][ns][9]
+  const float* poses;       // [B][S][6]
+  const float* gy;          // upstream gradient (device scalar) or nullptr
+  double* acc;              // [4 + B*S*12]
+  unsigned* counter;
+  float* losses_out;        // [5] or nullptr
+  float* gposes;            // [B][S][6] or nullptr
+  // loss weights per scale (host-computed in fp64, global batch in the denominators)
+  float inv_n3[SFM_MAX_SCALES];      // 1 / (Bg*3*h*w)
+  float inv_n1[SFM_MAX_SCALES];      // 1 / (Bg*h*w)
+  float sm_dx2[SFM_MAX_SCALES];      // smooth_reg/2^s / (Bg*h*(w-2))
+  float sm_mix[SFM_MAX_SCALES];      // smooth_reg/2^s / (Bg*(h-1)*(w-1))
+  float sm_dy2[SFM_MAX_SCALES];      // smooth_reg/2^s / (Bg*(h-2)*w)
+  float smooth_reg, exp_reg, ssim_rate;
+  int use_smooth;
+  // debug dumps (nullptr when unused)
+  float* dbg_P[SFM_MAX_SCALES];
+  int32_t* dbg_u0[SFM_MAX_SCALES];
+  int32_t* dbg_v0[SFM_MAX_SCALES];
+  uint8_t* dbg_inb[SFM_MAX_SCALES];
+};
+
+// mode bits for the launcher
+enum { SFM_MODE_EXP = 1, SFM_MODE_SSIM = 2, SFM_MODE_GRAD = 4, SFM_MODE_DEBUG = 8 };
+int sfm_launch_fused(SfmFusedParams& p, int mode, cudaStream_t stream);
+
+int sfm_launch_scale(float* const* ptrs, const long long* counts, int n, const float* gy, cudaStream_t stream);

@@ -1,0 +1,88 @@
+"""-m "not gpu": the C-ABI library loads, exports every symbol include/sfmloss.h declares, and
+validates arguments (no compute without a GPU) -- plus host-side checks of the Python mirror."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from sfm_learner_chainer_b200 import lib as L
+    return L
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'sfmloss.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(sfm_[a-z_0-9]+)\s*\(', hdr))
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+    so = lib.load()
+    for name in declared:
+        assert getattr(so, name) is not None
+    assert so.sfm_version() == 100
+
+
+def test_struct_layout_matches_header(lib):
+    assert C.sizeof(lib.SfmDesc) == 40
+    assert C.sizeof(lib.SfmInputs) == 8 * (3 + 4 + 1 + 4 + 2)
+    assert C.sizeof(lib.SfmGrads) == 8 * 9
+    assert C.sizeof(lib.SfmDebug) == 8 * 16
+
+
+def test_workspace_and_validation(lib):
+    so = lib.load()
+    d = lib.SfmDesc(4, 2, 128, 416, 4, 0, 0.1, 0.0, 0.15, 0)
+    n = so.sfm_workspace_bytes(C.byref(d))
+    pyr = 4 * 3 * 70720 * 16
+    assert pyr <= n <= pyr + 64 * 1024
+    for bad, code in [(lib.SfmDesc(0, 2, 128, 416, 4, 0, 0, 0, 0, 0), 'B=0'),
+                      (lib.SfmDesc(4, 9, 128, 416, 4, 0, 0, 0, 0, 0), 'S=9'),
+                      (lib.SfmDesc(4, 2, 16, 416, 4, 0, 0, 0, 0, 0), '2x52'),
+                      (lib.SfmDesc(4, 2, 128, 416, 5, 0, 0, 0, 0, 0), 'n_scales=5'),
+                      (lib.SfmDesc(4, 2, 128, 416, 4, 2, 0, 0, 0, 0), 'B_global=2')]:
+        assert so.sfm_workspace_bytes(C.byref(bad)) == 0
+        assert code in so.sfm_last_error().decode()
+    # argument errors come back as negative codes with a message, before any device work
+    inp = lib.SfmInputs()
+    rc = so.sfm_loss_forward(C.byref(d), C.byref(inp), C.c_void_p(16), None, C.c_void_p(256), None)
+    assert rc == lib.SFM_E_NULL_POINTER and b'NULL' in so.sfm_last_error()
+    rc = so.sfm_loss_forward(C.byref(d), C.byref(inp), None, None, None, None)
+    assert rc == lib.SFM_E_NULL_POINTER
+    assert so.sfm_warp_forward(0, 8, 8, None, None, None, None, None, None, None, None, None, None, None) == lib.SFM_E_INVALID_SHAPE
+    assert so.sfm_sampler_interp_forward(1, 3, 8, 8, 0, 4, None, None, None, None) == lib.SFM_E_INVALID_SHAPE
+    with pytest.raises(lib.SfmError):
+        lib.check(so.sfm_warp_backward(1, 8, 8, None, None, None, None, None, None, None, None, None, None))
+
+
+def test_no_cpu_fallback(lib):
+    """Host arrays are rejected: the product path never computes on the CPU."""
+    from sfm_learner_chainer_b200 import ViewSynthesisLoss, projective_inverse_warp, SpatialTransformerSamplerInterp
+    from sfm_learner_chainer_b200.synthetic import make_snippets
+    d = make_snippets(1, 2, 32, 104)
+    op = ViewSynthesisLoss(0.1, 0.0, 0.15)
+    with pytest.raises(TypeError, match='no CPU fallback'):
+        op.forward_backward(d['tgt'], d['src'], d['intrinsics'], d['disps'], d['poses'], d['logits'])
+    with pytest.raises(TypeError):
+        projective_inverse_warp(d['src'][:, 0], np.ones((1, 32 * 104), np.float32), d['poses'][:, 0], d['intrinsics'][:, 0])
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        SpatialTransformerSamplerInterp().forward_cpu((d['tgt'], d['tgt']))
+
+
+def test_product_package_does_not_import_oracle():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import sfm_learner_chainer_b200, sfm_learner_chainer_b200.torch_adapter, "
+            "sfm_learner_chainer_b200.chainer_adapter; "
+            "assert not [m for m in sys.modules if m.startswith('oracle')], 'oracle imported by product'" % ROOT)
+    subprocess.check_call([sys.executable, '-c', code])
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'sfm_learner_chainer_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f

@@ -1,0 +1,313 @@
+"""-m gpu: the CUDA path (through the C ABI) against the numpy oracle and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sfm_oracle as O
+from sfm_learner_chainer_b200.synthetic import make_snippets
+from tests.gpu_util import to_dev, dev_inputs, host, oracle_tables, assert_grad_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+FLAGSETS = {
+    'v1': dict(smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0),        # experiments/sfm_learner_v1.yml
+    'v1_ssim': dict(smooth_reg=0.1, exp_reg=0.0, ssim_rate=0.15),  # experiments/sfm_learner_v1_ssim.yml
+    'v1_odom': dict(smooth_reg=0.1, exp_reg=0.2, ssim_rate=0.0),   # experiments/sfm_learner_v1_odom.yml
+    'exp_ssim_rate': dict(smooth_reg=0.05, exp_reg=0.3, ssim_rate=0.25),  # exp branch wins, (1-ssim_rate) weight stays
+}
+
+
+def _op(flags, **kw):
+    from sfm_learner_chainer_b200 import ViewSynthesisLoss
+    return ViewSynthesisLoss(flags['smooth_reg'], flags['exp_reg'], flags['ssim_rate'], **kw)
+
+
+def _oracle(d, flags, **kw):
+    cfg = O.LossConfig(**flags)
+    return O.sfm_loss(d['tgt'], d['src'], d['intrinsics'], d['disps'], d['poses'], d['logits'], cfg, **kw)
+
+
+# ---------------------------------------------------------------- T1: integer work, bit exact
+@pytest.mark.parametrize('flagset', ['v1', 'v1_ssim'])
+@pytest.mark.parametrize('B,S,H,W,seed,harsh', [(2, 2, 32, 104, 0, False), (1, 4, 48, 160, 1, True),
+                                                (2, 2, 128, 416, 2, False), (1, 3, 40, 72, 3, True)])
+def test_indices_masks_and_warp_bit_exact(flagset, B, S, H, W, seed, harsh):
+    d = make_snippets(B, S, H, W, seed=seed, harsh=harsh, rough_disp=bool(seed & 1))
+    flags = FLAGSETS[flagset]
+    proj, kinv = oracle_tables(O, d)
+    L, _, dbg = _oracle(d, flags, want_grads=False, want_debug=True,
+                        proj_override=np.concatenate([proj, np.zeros_like(proj[..., :1, :])], -2), kinv_override=kinv)
+    g = dev_inputs(d)
+    losses, gd = _op(flags).forward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'],
+                                    proj=to_dev(proj), kinv=to_dev(kinv), debug=True)
+    for s in range(4):
+        np.testing.assert_array_equal(host(gd['u0'][s]), dbg['u0'][s], err_msg='u0 scale %d' % s)
+        np.testing.assert_array_equal(host(gd['v0'][s]), dbg['v0'][s], err_msg='v0 scale %d' % s)
+        np.testing.assert_array_equal(host(gd['inb'][s]).astype(bool), dbg['inb'][s], err_msg='inb scale %d' % s)
+        np.testing.assert_array_equal(host(gd['P'][s]), dbg['P'][s], err_msg='warped image scale %d' % s)
+    np.testing.assert_allclose(host(losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize('H,W', [(32, 104), (128, 416), (40, 72)])
+def test_pyramid_bit_exact(H, W):
+    d = make_snippets(2, 2, H, W, seed=4)
+    tp, sp = _op(FLAGSETS['v1']).pyramid(to_dev(d['tgt']), to_dev(d['src']))
+    for s in range(4):
+        h, w = H >> s, W >> s
+        np.testing.assert_array_equal(host(tp[s]), O.resize_images(d['tgt'], (h, w)))
+        ref = O.resize_images(d['src'].reshape(2, 6, H, W), (h, w)).reshape(2, 2, 3, h, w)
+        np.testing.assert_array_equal(host(sp[s]), ref)
+
+
+@pytest.mark.parametrize('harsh', [False, True])
+def test_device_tables_match_host_tables(harsh):
+    """device prologue (pose_vec2mat/euler2mat/proj_tgt_to_src/batch_inv) vs the oracle's tables."""
+    d = make_snippets(8, 4, 128, 416, seed=5, harsh=harsh)
+    d['poses'][0, 0, :3] = [3.5, -4.0, 0.3]          # exercises the clip to [-pi, pi] (transform.py:23)
+    proj, kinv = oracle_tables(O, d)
+    gp, gk = _op(FLAGSETS['v1']).build_tables(to_dev(d['poses']), to_dev(d['intrinsics']), 128, 416)
+    np.testing.assert_array_equal(host(gk), kinv)
+    # sin/cos are fp64-evaluated on both sides; allow a last-bit difference but report exactness
+    np.testing.assert_allclose(host(gp), proj, rtol=3e-7, atol=1e-9)
+    assert np.mean(host(gp) == proj) > 0.999
+
+
+# ---------------------------------------------------------------- T2/T3: end-to-end forward + backward
+@pytest.mark.parametrize('flagset', sorted(FLAGSETS))
+@pytest.mark.parametrize('B,S,H,W,seed,harsh', [(2, 2, 32, 104, 10, False), (2, 4, 32, 104, 11, False),
+                                                (1, 2, 48, 160, 12, True), (1, 3, 40, 72, 13, True),
+                                                (2, 2, 128, 416, 14, False)])
+def test_loss_and_gradients_match_oracle(flagset, B, S, H, W, seed, harsh):
+    d = make_snippets(B, S, H, W, seed=seed, harsh=harsh, rough_disp=bool(seed & 1))
+    flags = FLAGSETS[flagset]
+    L, G, _ = _oracle(d, flags)
+    g = dev_inputs(d)
+    op = _op(flags)
+    losses, grads = op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    np.testing.assert_allclose(host(losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)       # north star: rtol 1e-5
+    assert_grad_close(host(grads['gposes']), G['gpose'], what='gpose')                      # north star: rtol 1e-4
+    for s in range(4):
+        assert_grad_close(host(grads['gdisps'][s]), G['gdisp'][s], what='gdisp[%d]' % s)
+        if G['glogits'] is not None:
+            assert_grad_close(host(grads['glogits'][s]), G['glogits'][s], what='glogits[%d]' % s)
+    assert (grads['glogits'] is not None) == (G['glogits'] is not None)
+    # forward-only and recomputing-backward entry points agree with the fused pass
+    l2 = op.forward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    np.testing.assert_allclose(host(l2), host(losses), rtol=1e-6, atol=1e-9)
+    gy = to_dev(np.array([2.5], np.float32))
+    g2 = op.backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'], gy=gy)
+    np.testing.assert_allclose(host(g2['gposes']), 2.5 * host(grads['gposes']), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(host(g2['gdisps'][0]), 2.5 * host(grads['gdisps'][0]), rtol=2e-5, atol=1e-9)
+    ref = [host(x).copy() for x in grads['gdisps']]
+    op.scale_grads(grads, gy, B, S, H, W)
+    np.testing.assert_allclose(host(grads['gdisps'][1]), 2.5 * ref[1], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('name', ['v1', 'v1_ssim', 'v1_odom', 'v1_ssim_harsh', 'v1_odom_harsh'])
+def test_against_golden_fixtures(name):
+    """CUDA path vs outputs of the reference's own source files (tests/golden/make_golden.py)."""
+    gd = np.load(os.path.join(GOLD, 'loss_%s.npz' % name))
+    sm, ex, ss = [float(v) for v in gd['flags']]
+    op = _op(dict(smooth_reg=sm, exp_reg=ex, ssim_rate=ss))
+    disps = [to_dev(gd['disp%d' % s]) for s in range(4)]
+    logits = [to_dev(gd['logits%d' % s]) for s in range(4)]
+    losses, grads = op.forward_backward(to_dev(gd['tgt']), to_dev(gd['src']), to_dev(gd['intrinsics']), disps,
+                                        to_dev(gd['poses']), logits)
+    np.testing.assert_allclose(host(losses), gd['losses_f64'], rtol=1e-5, atol=1e-9)
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+    # the fp64 run of the reference is "true math": fp32 floor flips move single pixels,
+    # so this comparison is norm-wise; the element-wise bar is test_loss_and_gradients_match_oracle.
+    assert rel(host(grads['gposes']), gd['gpose_f64']) < 5e-3
+    for s in range(4):
+        assert rel(host(grads['gdisps'][s]), gd['gdisp%d_f64' % s]) < 5e-3
+        if ex:
+            assert rel(host(grads['glogits'][s]), gd['glogits%d_f64' % s]) < 1e-4
+
+
+# ---------------------------------------------------------------- stage API
+@pytest.mark.parametrize('h,w,harsh', [(32, 104, False), (128, 416, True), (9, 7, True)])
+def test_projective_inverse_warp_stage(h, w, harsh):
+    from sfm_learner_chainer_b200 import projective_inverse_warp, projective_inverse_warp_backward
+    rs = np.random.RandomState(3)
+    N = 3
+    d = make_snippets(N, 1, h * 8, w * 8, seed=21, harsh=harsh)
+    imgs = O.resize_images(d['src'][:, 0], (h, w)).astype(np.float32)
+    depth = (1.0 / O.resize_images(d['disps'][0], (h, w))).reshape(N, h * w).astype(np.float32)
+    K = d['intrinsics'][:, 3]
+    pose = d['poses'][:, 0]
+    Pref, rec = O.projective_inverse_warp(imgs, depth, pose, K)
+    proj = np.ascontiguousarray(rec['proj'][:, :3, :])
+    out, u0, v0, inb = projective_inverse_warp(to_dev(imgs), to_dev(depth), to_dev(pose), to_dev(K),
+                                               proj=to_dev(proj), kinv=to_dev(rec['Kinv']), return_indices=True)
+    np.testing.assert_array_equal(host(u0).reshape(N, -1), rec['taps']['u0'])
+    np.testing.assert_array_equal(host(v0).reshape(N, -1), rec['taps']['v0'])
+    np.testing.assert_array_equal(host(inb).reshape(N, -1).astype(bool), rec['grid']['inx'] & rec['grid']['iny'])
+    np.testing.assert_array_equal(host(out), Pref)
+    # the reference passes depth broadcast to 3 rows (base_model.py:81-84)
+    out3 = projective_inverse_warp(to_dev(imgs), to_dev(np.broadcast_to(depth[:, None], (N, 3, h * w)).copy()),
+                                   to_dev(pose), to_dev(K))
+    np.testing.assert_allclose(host(out3), Pref, rtol=0, atol=2e-5)
+    # backward against the oracle's chain
+    gy = rs.uniform(-1, 1, (N, 3, h, w)).astype(np.float32)
+    t64 = {k: (v.astype(np.float64) if v.dtype.kind == 'f' else v) for k, v in rec['taps'].items()}
+    gxn, gyn = O.spatial_transformer_sampler_grad(t64, gy.reshape(N, 3, -1).astype(np.float64), h, w)
+    gr = rec['grid']
+    gxn = gxn * np.where(gr['inx'], 1.0, 2.0)
+    gyn = gyn * np.where(gr['iny'], 1.0, 2.0)
+    z = gr['z'].astype(np.float64)
+    q = gr['q'].astype(np.float64)
+    with np.errstate(all='ignore'):
+        gq = np.stack([gxn / (z * float(gr['hw'])), gyn / (z * float(gr['hh'])),
+                       -(gxn * q[:, 0] / float(gr['hw']) + gyn * q[:, 1] / float(gr['hh'])) / (z * z)], 1)
+    gq = np.where(rec['taps']['any_valid'][:, None], gq, 0.0)
+    gcam = np.einsum('nkp,nkj->njp', gq, rec['proj'][:, :3, :3].astype(np.float64))
+    gdepth_ref = np.sum(gcam * rec['ray'].astype(np.float64), axis=1)
+    cam4 = np.concatenate([rec['cam'].astype(np.float64), np.ones((N, 1, h * w))], 1)
+    dP = np.einsum('nkp,njp->nkj', gq, cam4)
+    gpose_ref, _ = O._pose_backward(pose, [K], [dP])
+    gdepth, gposes, gimgs = projective_inverse_warp_backward(to_dev(imgs), to_dev(depth), to_dev(pose), to_dev(K),
+                                                             to_dev(gy), want_gimgs=True)
+    assert_grad_close(host(gdepth), gdepth_ref, what='gdepth')
+    assert_grad_close(host(gposes), gpose_ref, what='gposes')
+    # gimgs: adjoint identity <gy, warp(img)> == <gimgs, img> (the warp is linear in the image)
+    lhs = float(np.sum(gy.astype(np.float64) * Pref))
+    rhs = float(np.sum(host(gimgs).astype(np.float64) * imgs))
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_sampler_interp_matches_reference_fixture():
+    from sfm_learner_chainer_b200 import SpatialTransformerSamplerInterp, spatial_transformer_sampler_interp
+    g = np.load(os.path.join(GOLD, 'interp_sampler.npz'))
+    fn = SpatialTransformerSamplerInterp()
+    x, grid, gy = to_dev(g['x']), to_dev(g['grid']), to_dev(g['gy'])
+    y, = fn.forward_gpu((x, grid))
+    np.testing.assert_array_equal(host(y), g['y'])
+    np.testing.assert_array_equal(host(spatial_transformer_sampler_interp(x, grid)), g['y'])
+    gx, ggrid = fn.backward_gpu((x, grid), (gy,))
+    np.testing.assert_array_equal(host(gx), g['gx'])
+    np.testing.assert_allclose(host(ggrid), g['ggrid'], rtol=1e-6, atol=1e-6)
+    with pytest.raises(TypeError):
+        fn.forward_gpu((x, to_dev(g['grid'][:, :1])))          # grid.shape[1] != 2 (interp.py:22)
+
+
+# ---------------------------------------------------------------- properties at full size
+def test_identity_pose_and_all_out_of_view():
+    d = make_snippets(2, 2, 128, 416, seed=30)
+    d['poses'][:] = 0
+    g = dev_inputs(d)
+    op = _op(FLAGSETS['v1'])
+    _, dbg = op.forward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'], debug=True)
+    P = host(dbg['P'][0])
+    inb = host(dbg['inb'][0]).astype(bool)
+    assert inb[:, :, 1:-1, 1:-1].all()
+    m = np.broadcast_to(inb[:, :, None], P.shape)
+    np.testing.assert_allclose(P[m], d['src'][m], atol=5e-4)
+    # a huge sideways translation throws every pixel out of view: photometric terms are exactly 0
+    d['poses'][:, :, 3] = 1e4
+    g = dev_inputs(d)
+    losses, grads = _op(FLAGSETS['v1_ssim']).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'],
+                                                              g['poses'], g['logits'])
+    lv = host(losses)
+    assert lv[1] == 0.0 and lv[4] == 0.0 and lv[2] > 0
+    assert not host(grads['gposes']).any()
+
+
+@pytest.mark.parametrize('cfg', ['cfg4', 'cfg2'])
+def test_shard_sum_equals_full_batch_at_full_size(cfg):
+    """Size-independent property at BASELINE.json's shapes: snippet shards (B_global = full batch) sum to
+    the full-batch losses and reproduce its gradients -- the multi-GPU decomposition."""
+    from sfm_learner_chainer_b200.synthetic import CONFIGS
+    c = dict(CONFIGS[cfg])
+    B, S, H, W = c.pop('B'), c.pop('S'), c.pop('H'), c.pop('W')
+    B = min(B, 8)
+    d = make_snippets(B, S, H, W, seed=31)
+    g = dev_inputs(d)
+    lf, gf = _op(c).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    acc = np.zeros(5)
+    half = B // 2
+    for lo in (0, half):
+        sl = slice(lo, lo + half)
+        ls, gs = _op(c, B_global=B).forward_backward(
+            g['tgt'][sl].contiguous(), g['src'][sl].contiguous(), g['intrinsics'][sl].contiguous(),
+            [x[sl].contiguous() for x in g['disps']], g['poses'][sl].contiguous(),
+            [x[sl].contiguous() for x in g['logits']])
+        acc += host(ls).astype(np.float64)
+        np.testing.assert_allclose(host(gs['gposes']), host(gf['gposes'])[sl], rtol=1e-5, atol=1e-8)
+        np.testing.assert_array_equal(host(gs['gdisps'][0]), host(gf['gdisps'][0])[sl])
+    np.testing.assert_allclose(acc, host(lf), rtol=2e-6)
+
+
+def test_batch_permutation_equivariance():
+    d = make_snippets(4, 2, 64, 208, seed=32)
+    perm = np.array([2, 0, 3, 1])
+    flags = FLAGSETS['v1_ssim']
+    g = dev_inputs(d)
+    l0, g0 = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    dp = dict(tgt=d['tgt'][perm], src=d['src'][perm], intrinsics=d['intrinsics'][perm],
+              disps=[x[perm] for x in d['disps']], poses=d['poses'][perm], logits=[x[perm] for x in d['logits']])
+    g = dev_inputs(dp)
+    l1, g1 = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    np.testing.assert_allclose(host(l1), host(l0), rtol=1e-6)
+    np.testing.assert_array_equal(host(g1['gdisps'][0]), host(g0['gdisps'][0])[perm])
+    np.testing.assert_allclose(host(g1['gposes']), host(g0['gposes'])[perm], rtol=1e-5, atol=1e-9)
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    import ctypes as C
+    from sfm_learner_chainer_b200 import lib as L
+    d = make_snippets(2, 2, 64, 208, seed=33)
+    flags = FLAGSETS['v1_odom']
+    g = dev_inputs(d)
+    l_dev, g_dev = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    lib = L.load()
+    desc = L.SfmDesc(2, 2, 64, 208, 4, 0, flags['smooth_reg'], flags['exp_reg'], flags['ssim_rate'], 0)
+    ctx = C.c_void_p()
+    L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
+    try:
+        inp, grads = L.SfmInputs(), L.SfmGrads()
+        inp.tgt, inp.src = d['tgt'].ctypes.data, d['src'].ctypes.data
+        inp.intrinsics, inp.poses = d['intrinsics'].ctypes.data, d['poses'].ctypes.data
+        gd = [np.empty_like(x) for x in d['disps']]
+        gl = [np.empty_like(x) for x in d['logits']]
+        gp = np.empty_like(d['poses'])
+        for s in range(4):
+            inp.disps[s], inp.logits[s] = d['disps'][s].ctypes.data, d['logits'][s].ctypes.data
+            grads.gdisps[s], grads.glogits[s] = gd[s].ctypes.data, gl[s].ctypes.data
+        grads.gposes = gp.ctypes.data
+        losses = np.empty(5, np.float32)
+        L.check(lib.sfm_loss_step_host(ctx, C.byref(inp), losses.ctypes.data, C.byref(grads)))
+    finally:
+        lib.sfm_host_ctx_destroy(ctx)
+    np.testing.assert_allclose(losses, host(l_dev), rtol=1e-6)
+    np.testing.assert_allclose(gp, host(g_dev['gposes']), rtol=1e-5, atol=1e-9)
+    for s in range(4):
+        np.testing.assert_array_equal(gd[s], host(g_dev['gdisps'][s]))
+        np.testing.assert_array_equal(gl[s], host(g_dev['glogits'][s]))
+
+
+def test_torch_autograd_bridge_and_model_surface():
+    """SFMLearner.__call__ surface (base_model.py:48-124) with stub nets: loss, five reports, gradients
+    reaching the producers of pred_disps / pred_poses / pred_maskes."""
+    import torch
+    from sfm_learner_chainer_b200 import SFMLearner
+    d = make_snippets(2, 2, 32, 104, seed=34)
+    flags = FLAGSETS['v1_odom']
+    L, G, _ = _oracle(d, flags)
+    g = dev_inputs(d)
+    disps = [x.clone().requires_grad_(True) for x in g['disps']]
+    poses = [g['poses'][:, i].clone().requires_grad_(True) for i in range(2)]
+    masks = [x.clone().requires_grad_(True) for x in g['logits']]
+    reports = {}
+    model = SFMLearner(dict(seq_len=3, **flags), None, disp_net=lambda t: disps,
+                       pose_net=lambda t, s, do_exp=True: (tuple(poses), masks if do_exp else None),
+                       reporter=lambda kv, obs: reports.update(kv))
+    loss = model(g['tgt'], g['src'], g['intrinsics'], g['intrinsics'])
+    (3.0 * loss).backward()
+    assert sorted(reports) == sorted(O.LOSS_KEYS)
+    np.testing.assert_allclose(float(loss), L['total_loss'], rtol=1e-5)
+    np.testing.assert_allclose(float(reports['ssim_loss']), 0.0)
+    assert_grad_close(host(torch.stack([p.grad for p in poses], 1)), 3.0 * G['gpose'], what='gpose via autograd')
+    assert_grad_close(host(disps[2].grad), 3.0 * G['gdisp'][2], what='gdisp via autograd')
+    assert_grad_close(host(masks[1].grad), 3.0 * G['glogits'][1], what='glogits via autograd')
