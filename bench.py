@@ -1,0 +1,514 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd warp+photometric loss throughput of the view-synthesis loss path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (image pyramid + fused loss forward+backward, single sweep)
+over one batch of synthetic KITTI-shaped snippets.  Default workload = BASELINE.json configs[1]
+(sfm_learner_v1_ssim.yml loss path: SSIM + L1 + smoothness, B=4, S=2, 128x416, 4 scales) per GPU;
+under N GPUs the batch is sharded by snippet (weak scaling: 4 snippets per rank, B_global = 4N), the
+only exchange being the 5-float loss-partial allreduce (asynchronous, NCCL).
+
+Prints ONE JSON line (rank 0).  Keys beyond the driver's contract:
+  roofline       dominant kernel (fused loss) vs the measured HBM copy peak, timed live with CUDA events
+  roofline_step  whole step vs the strict byte model (SURVEY 8(d) "A-strict")
+  cpu_baseline   the numpy oracle (port of the reference's numpy/Chainer CPU path) on this box's cores
+  e2e            same metric through the C-ABI host-buffer entry point (H2D + kernels + D2H per step)
+  other_configs  device-timed numbers for the remaining single-GPU BASELINE shapes (cfg1, cfg4, cfg5)
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+from sfm_learner_chainer_b200.synthetic import make_snippets, CONFIGS
+
+METRIC = 'fwd+bwd warp+photometric loss Mpix/s at 128x416'
+UNIT = 'Mpix/s'
+FALLBACK_HBM_GBS = 6650.0
+
+
+def pyramid_pixels(H, W, n_scales=4):
+    return sum((H >> s) * (W >> s) for s in range(n_scales))
+
+
+def bytes_strict(B, S, H, W, exp):
+    """SURVEY 8(d) A-strict: full-res images once + disp r/w + logits r/w + poses + K."""
+    pix = pyramid_pixels(H, W)
+    return 4 * (B * (1 + S) * 3 * H * W + 2 * B * pix + (2 * B * S * pix if exp else 0)) + 48 * B * S + 144 * B
+
+
+def bytes_fused_kernel(B, S, H, W, exp):
+    """SURVEY 8(d) secondary model (pyramid as the kernel's input): 4*B*sum_hw*(3 + 3S + 2 + exp*2S)."""
+    return 4 * B * pyramid_pixels(H, W) * (3 + 3 * S + 2 + (2 * S if exp else 0))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the numpy oracle on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_run(cfg_name, n_iters, threads):
+    """Times fwd+bwd of the numpy restatement of the reference path, sharded by snippet over a thread
+    pool (numpy releases the GIL in its array loops).  Returns seconds per step (all B snippets)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import sfm_oracle as O                                  # the timed CPU baseline
+    c = dict(CONFIGS[cfg_name])
+    B, S, H, W = c.pop('B'), c.pop('S'), c.pop('H'), c.pop('W')
+    d = make_snippets(B, S, H, W, seed=0)
+    cfg = O.LossConfig(B_global=B, **c)
+
+    def one(b):
+        sl = slice(b, b + 1)
+        return O.sfm_loss(d['tgt'][sl], d['src'][sl], d['intrinsics'][sl], [x[sl] for x in d['disps']],
+                          d['poses'][sl], [x[sl] for x in d['logits']], cfg)[0]
+
+    threads = max(1, min(threads, B))
+    times = []
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(min(B, threads))))                        # warm-up (page-in, caches)
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(B)))
+            times.append(time.perf_counter() - t0)
+    return float(np.median(times)), threads, (B, S, H, W)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    ncpu = os.cpu_count() or 1
+    c = CONFIGS[args.config]
+    sec, threads, (B, S, H, W) = cpu_oracle_run(args.config, max(1, args.steps), ncpu)
+    pix = B * pyramid_pixels(H, W)
+    val = pix / sec / 1e6
+    sample = '%d full %s steps (B=%d, S=%d, %dx%d, 4 scales), snippets sharded over %d threads' % (
+        max(1, args.steps), args.config, B, S, H, W, threads)
+    line = dict(impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=max(1, args.steps),
+                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic',
+                config=dict(workload='%s: %s' % (args.config, describe(args.config)), B=B, S=S, H=H, W=W,
+                            note='numpy restatement (oracle/) of the reference numpy/Chainer CPU path; '
+                                 'chainer==4.0.0b1 is not installable in this image'),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind='port', sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+def describe(name):
+    c = CONFIGS[name]
+    return 'B=%d S=%d %dx%d 4 scales, smooth_reg=%g exp_reg=%g ssim_rate=%g' % (
+        c['B'], c['S'], c['H'], c['W'], c['smooth_reg'], c['exp_reg'], c['ssim_rate'])
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks (pynvml sampler thread)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        self.samples = []
+        self.ok = False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                                          # noqa: BLE001
+            self.err = repr(e)
+            self.max_mhz = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample(self):
+        nv = self.nv
+        return (time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self._sample())
+            except Exception:                                           # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvml unavailable: %s' % getattr(self, 'err', '')])
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or [s for s in self.samples if s[0] >= t0][:1] \
+            or self.samples[-1:]
+        mhz = float(np.median([s[1] for s in inside])) if inside else None
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = [n for b, n in self.REASONS.items() if mask & b and n != 'gpu_idle']
+        return dict(sm_mhz=mhz, sm_max_mhz=float(self.max_mhz), reasons=reasons, samples=len(inside))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+class Workload(object):
+    """Pre-packed C-ABI calls over `nsets` rotating buffer sets (inputs AND outputs), so that with a
+    working set below the 126 MB L2 consecutive steps still touch HBM."""
+
+    def __init__(self, cfg_name, device, B_global=None, min_rotation_bytes=None, B_local=None, seed=0):
+        import torch
+        from sfm_learner_chainer_b200 import lib as L
+        self.torch, self.L = torch, L
+        self.lib = L.load()
+        c = dict(CONFIGS[cfg_name])
+        B, S, H, W = c.pop('B'), c.pop('S'), c.pop('H'), c.pop('W')
+        if B_local:
+            B = B_local
+        self.B, self.S, self.H, self.W, self.flags = B, S, H, W, c
+        self.exp = c['exp_reg'] != 0
+        self.A_strict = bytes_strict(B, S, H, W, self.exp)
+        self.A_kernel = bytes_fused_kernel(B, S, H, W, self.exp)
+        self.pix = B * pyramid_pixels(H, W)
+        l2 = torch.cuda.get_device_properties(device).L2_cache_size
+        rot = min_rotation_bytes if min_rotation_bytes is not None else 2 * l2
+        self.nsets = max(2, int(math.ceil(rot / float(self.A_strict))) + 1)
+        self.l2_bytes = l2
+        nb = min(B, 4)
+        base = make_snippets(nb, S, H, W, seed=seed)
+        rep = lambda a: np.ascontiguousarray(np.concatenate([a] * (B // nb) + [a[:B % nb]], 0)) if B != nb else a
+        self.host = dict(tgt=rep(base['tgt']), src=rep(base['src']), intrinsics=rep(base['intrinsics']),
+                         disps=[rep(x) for x in base['disps']], poses=rep(base['poses']),
+                         logits=[rep(x) for x in base['logits']])
+        self.desc = L.SfmDesc(B, S, H, W, 4, int(B_global or 0), c['smooth_reg'], c['exp_reg'], c['ssim_rate'], 0)
+        nws = self.lib.sfm_workspace_bytes(C.byref(self.desc))
+        dev = lambda a: torch.from_numpy(a).to(device)
+        self.sets = []
+        for k in range(self.nsets):
+            t = dict(tgt=dev(self.host['tgt']), src=dev(self.host['src']), K=dev(self.host['intrinsics']),
+                     disps=[dev(x) for x in self.host['disps']], poses=dev(self.host['poses']),
+                     logits=[dev(x) for x in self.host['logits']] if self.exp else None,
+                     gdisps=[torch.empty_like(dev(x)) for x in self.host['disps']],
+                     gposes=torch.empty((B, S, 6), device=device),
+                     glogits=[torch.empty((B, S, H >> s, W >> s), device=device) for s in range(4)] if self.exp else None,
+                     losses=torch.zeros(8, device=device),
+                     ws=torch.empty(nws + 256, dtype=torch.uint8, device=device))
+            inp, g = L.SfmInputs(), L.SfmGrads()
+            inp.tgt, inp.src, inp.intrinsics, inp.poses = (t['tgt'].data_ptr(), t['src'].data_ptr(), t['K'].data_ptr(),
+                                                           t['poses'].data_ptr())
+            g.gposes = t['gposes'].data_ptr()
+            for s in range(4):
+                inp.disps[s] = t['disps'][s].data_ptr()
+                g.gdisps[s] = t['gdisps'][s].data_ptr()
+                if self.exp:
+                    inp.logits[s] = t['logits'][s].data_ptr()
+                    g.glogits[s] = t['glogits'][s].data_ptr()
+            t['inp'], t['g'] = inp, g
+            t['wsp'] = C.c_void_p((t['ws'].data_ptr() + 255) // 256 * 256)
+            self.sets.append(t)
+        self.graphs = None
+
+    def launch(self, k, stream):
+        t = self.sets[k % self.nsets]
+        rc = self.lib.sfm_loss_forward_backward(C.byref(self.desc), C.byref(t['inp']), C.c_void_p(t['losses'].data_ptr()),
+                                                C.byref(t['g']), t['wsp'], C.c_void_p(stream))
+        if rc:
+            self.L.check(rc)
+
+    def capture(self):
+        """One CUDA graph per buffer set (prep + fused kernel nodes): replays cost one launch each."""
+        torch = self.torch
+        self.graphs = []
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(self.nsets):
+                self.launch(k, side.cuda_stream)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for k in range(self.nsets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.launch(k, torch.cuda.current_stream().cuda_stream)
+            self.graphs.append(g)
+        torch.cuda.synchronize()
+
+    def step(self, k):
+        if self.graphs is not None:
+            self.graphs[k % self.nsets].replay()
+        else:
+            self.launch(k, self.torch.cuda.current_stream().cuda_stream)
+
+    def time_steps(self, steps, warmup, per_step=None):
+        torch = self.torch
+        for k in range(warmup):
+            self.step(k)
+            if per_step:
+                per_step(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(steps):
+            self.step(warmup + k)
+            if per_step:
+                per_step(warmup + k)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        return e0.elapsed_time(e1) / steps, t0, t1
+
+    def time_fused_kernel(self, n=200):
+        """Average device duration of the fused loss kernel alone (events recorded by the library right
+        around its launch, on the launching stream)."""
+        torch = self.torch
+        st = torch.cuda.current_stream()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for k in range(5):
+            self.launch(k, st.cuda_stream)
+        torch.cuda.synchronize()
+        # torch creates its cudaEvent_t lazily on first record(); record once so the handles exist
+        for a, b in evs:
+            a.record(); b.record()
+        torch.cuda.synchronize()
+        for k, (a, b) in enumerate(evs):
+            self.lib.sfm_set_kernel_events(C.c_void_p(a.cuda_event), C.c_void_p(b.cuda_event))
+            self.launch(k, st.cuda_stream)
+        self.lib.sfm_set_kernel_events(None, None)
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return float(np.mean(ts)), float(ts[len(ts) // 2])
+
+
+def run_e2e(cfg_name, steps, device):
+    """Same metric through the host-buffer C-ABI entry point: pinned host inputs -> H2D -> pyramid + fused
+    fwd+bwd -> D2H of the 5 losses and every gradient, each step."""
+    import torch
+    from sfm_learner_chainer_b200 import lib as L
+    lib = L.load()
+    c = dict(CONFIGS[cfg_name])
+    B, S, H, W = c.pop('B'), c.pop('S'), c.pop('H'), c.pop('W')
+    exp = c['exp_reg'] != 0
+    d = make_snippets(B, S, H, W, seed=1)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hp = dict(tgt=pin(d['tgt']), src=pin(d['src']), K=pin(d['intrinsics']), poses=pin(d['poses']),
+              disps=[pin(x) for x in d['disps']], logits=[pin(x) for x in d['logits']],
+              gdisps=[pin(np.empty_like(x)) for x in d['disps']], glogits=[pin(np.empty_like(x)) for x in d['logits']],
+              gposes=pin(np.empty_like(d['poses'])), losses=pin(np.zeros(8, np.float32)))
+    desc = L.SfmDesc(B, S, H, W, 4, 0, c['smooth_reg'], c['exp_reg'], c['ssim_rate'], 0)
+    ctx = C.c_void_p()
+    L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
+    inp, g = L.SfmInputs(), L.SfmGrads()
+    inp.tgt, inp.src, inp.intrinsics, inp.poses = hp['tgt'].data_ptr(), hp['src'].data_ptr(), hp['K'].data_ptr(), hp['poses'].data_ptr()
+    g.gposes = hp['gposes'].data_ptr()
+    h2d = hp['tgt'].numel() * 4 + hp['src'].numel() * 4 + hp['K'].numel() * 4 + hp['poses'].numel() * 4
+    d2h = 5 * 4 + hp['gposes'].numel() * 4
+    for s in range(4):
+        inp.disps[s], g.gdisps[s] = hp['disps'][s].data_ptr(), hp['gdisps'][s].data_ptr()
+        h2d += hp['disps'][s].numel() * 4
+        d2h += hp['gdisps'][s].numel() * 4
+        if exp:
+            inp.logits[s], g.glogits[s] = hp['logits'][s].data_ptr(), hp['glogits'][s].data_ptr()
+            h2d += hp['logits'][s].numel() * 4
+            d2h += hp['glogits'][s].numel() * 4
+    try:
+        for _ in range(3):
+            L.check(lib.sfm_loss_step_host(ctx, C.byref(inp), C.c_void_p(hp['losses'].data_ptr()), C.byref(g)))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            L.check(lib.sfm_loss_step_host(ctx, C.byref(inp), C.c_void_p(hp['losses'].data_ptr()), C.byref(g)))
+        sec = (time.perf_counter() - t0) / steps
+    finally:
+        lib.sfm_host_ctx_destroy(ctx)
+    return B * pyramid_pixels(H, W) / sec / 1e6, h2d, d2h, float(hp['losses'][0])
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the view-synthesis loss path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    n_gpus = world
+    peak, peak_src = measured_peak()
+
+    c = CONFIGS[args.config]
+    wl = Workload(args.config, device, B_global=c['B'] * world)
+    if not args.no_graph:
+        wl.capture()
+
+    # loss partials: one 5-float allreduce per step, asynchronous on NCCL's stream
+    pending = []
+
+    def per_step(k):
+        if world > 1:
+            pending.append(dist.all_reduce(wl.sets[k % wl.nsets]['losses'][:5], async_op=True))
+            if len(pending) > 64:
+                pending.pop(0).wait()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms, t0, t1 = wl.time_steps(args.steps, args.warmup, per_step if world > 1 else None)
+    for w in pending:
+        w.wait()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # keep the GPU busy a little longer if the timed region was too short for a clock sample
+    if t1 - t0 < 0.05:
+        tt = time.perf_counter()
+        k = 0
+        while time.perf_counter() - tt < 0.1:
+            wl.step(k)
+            k += 1
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+    sampler.stop()
+    clocks = sampler.summary(t0, t1)
+
+    total_pix = wl.pix * world
+    value = total_pix / (ms * 1e-3) / 1e6
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='%s: %s' % (args.config, describe(args.config)), per_gpu_batch=wl.B,
+                            global_batch=wl.B * world, sources=wl.S, H=wl.H, W=wl.W, n_scales=4,
+                            parallelism='snippet-sharded x%d, async 5-float loss allreduce' % world if world > 1 else 'single GPU',
+                            l2_policy='inputs+outputs rotated over %d buffer sets (%.0f MB > 2 x L2 %.0f MB)' % (
+                                wl.nsets, wl.nsets * wl.A_strict / 1e6, wl.l2_bytes / 1e6),
+                            launch='CUDA graph replay (prep + fused kernel nodes)' if not args.no_graph else 'direct C-ABI calls',
+                            units='target-pyramid pixels = B * sum_s h_s*w_s (%d per step per GPU)' % wl.pix),
+                clocks=clocks, gpu_launches=2 * args.steps)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (fused loss), events around the kernel itself
+        k_mean, k_med = wl.time_fused_kernel(200)
+        ach = wl.A_kernel / (k_mean * 1e-3) / 1e9
+        line['roofline'] = dict(bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                                kernel='sfm_fused_%s_kernel' % ('ssim' if (c['ssim_rate'] and not c['exp_reg']) else 'l1'),
+                                kernel_us=k_mean * 1e3, kernel_us_median=k_med * 1e3,
+                                algorithmic_bytes=wl.A_kernel, peak_source=peak_src,
+                                byte_model='4*B*sum_hw*(3 + 3S + 2 + exp*2S): NHWC4 pyramid in, disp in, gdisp out (+logits/glogits)',
+                                note='at B=4 the roofline time is ~2 us (below launch latency): latency-bound; '
+                                     'see other_configs for the bandwidth-relevant shapes')
+        ach_s = wl.A_strict / (ms * 1e-3) / 1e9
+        line['roofline_step'] = dict(bound='hbm', achieved=ach_s, peak=peak, unit='GB/s', frac=ach_s / peak,
+                                     algorithmic_bytes=wl.A_strict,
+                                     byte_model='A-strict: full-res images once + disp r/w + logits r/w + poses + K')
+        line['step_share_of_fused_kernel'] = k_mean / ms if world == 1 else None
+    if world == 1:
+        # ---- e2e through the host-buffer C-ABI entry point
+        e2e_steps = max(5, min(200, args.steps))
+        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device)
+        line['e2e'] = dict(value=ev, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
+                           api='sfm_loss_step_host (pinned host buffers; H2D, pyramid + fused fwd+bwd, D2H of losses and gradients)')
+        # ---- other single-GPU BASELINE shapes, device timed
+        if not args.no_other:
+            others = {}
+            del wl
+            torch.cuda.empty_cache()
+            for name in ('cfg1', 'cfg4', 'cfg5'):
+                if name == args.config:
+                    continue
+                w2 = Workload(name, device)
+                w2.capture()
+                oms, _, _ = w2.time_steps(50, 5)
+                km, _ = w2.time_fused_kernel(50)
+                others[name] = dict(workload=describe(name), ms_per_step=oms, value=w2.pix / (oms * 1e-3) / 1e6, unit=UNIT,
+                                    step_frac_of_hbm_peak=w2.A_strict / (oms * 1e-3) / 1e9 / peak,
+                                    fused_kernel_us=km * 1e3,
+                                    fused_kernel_frac_of_hbm_peak=w2.A_kernel / (km * 1e-3) / 1e9 / peak)
+                del w2
+                torch.cuda.empty_cache()
+            line['other_configs'] = others
+        # ---- CPU baseline: bounded sample of the same workload on the host cores
+        if not args.no_cpu:
+            n_iters = 12 if args.config in ('cfg1', 'cfg2') else 1
+            sec, threads, (B, S, H, W) = cpu_oracle_run(args.config, n_iters, 1)
+            line['cpu_baseline'] = dict(value=B * pyramid_pixels(H, W) / sec / 1e6, unit=UNIT, cores=threads, kind='port',
+                                        sample='%d full %s steps of the numpy oracle (scalar port, 1 thread), median' % (n_iters, args.config),
+                                        ms_per_step=sec * 1e3)
+    else:
+        # e2e at N GPUs: every rank runs the host-buffer path on its shard; aggregate = sum / max time
+        e2e_steps = max(5, min(100, args.steps))
+        dist.barrier()
+        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device)
+        t = torch.tensor([wl.pix / ev], device=device)      # us per step on this rank (pix / Mpix/s)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line['e2e'] = dict(value=total_pix / float(t.item()), unit=UNIT, h2d_bytes_per_step=h2d * world,
+                           d2h_bytes_per_step=d2h * world, steps=e2e_steps,
+                           api='sfm_loss_step_host on every rank (its snippet shard)')
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
+    ap.add_argument('--no-graph', action='store_true', help='direct C-ABI calls instead of CUDA graph replay')
+    ap.add_argument('--no-other', action='store_true', help='skip the other_configs sweep')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        if args.steps > 20:
+            args.steps = 20            # bounded sample: each step is ~0.2-0.8 s of host work
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

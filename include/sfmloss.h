@@ -135,6 +135,11 @@ int sfm_loss_forward_backward(const SfmDesc* desc, const SfmInputs* in, float* l
 /* grads *= *gy (device scalar).  No-op on the device when *gy == 1. */
 int sfm_scale_grads(const SfmDesc* desc, const float* gy, const SfmGrads* grads, void* stream);
 
+/* Profiling hook (bench.py's roofline measurement): while set (non-NULL cudaEvent_t handles), every
+ * sfm_loss_* call on this thread records `start` right before and `stop` right after the fused loss
+ * kernel, on the call's stream.  Pass NULL, NULL to clear. */
+int sfm_set_kernel_events(void* start_event, void* stop_event);
+
 /* Image pyramid only (F.resize_images from full resolution, base_model.py:70-72) into the workspace;
  * sfm_pyramid_export copies one level back out as NCHW for tests:
  * tgt_out (B,3,h,w), src_out (B,S,3,h,w). */

@@ -33,6 +33,7 @@ def build(force=False, verbose=False):
     cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-Xcompiler', '-fPIC', '-shared', '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
            '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get('SFM_NVCC_FLAGS', '').split()      # development knob, e.g. -DSFM_MINB=16
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -32,7 +32,7 @@ void sfm_set_error(const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------
 struct SfmWsLayout {
   size_t off_tgt[SFM_MAX_SCALES];  // float4 [B][h][w]       target pyramid, NHWC4 (RGB + zero pad)
-  size_t off_src[SFM_MAX_SCALES];  // float4 [B][S][h][w]    source pyramid, NHWC4
+  size_t off_src[SFM_MAX_SCALES];  // float4 [B][S][h][w]    source pyramid, NHWC4; element [-1] is a zero guard
   size_t off_proj;                 // float  [B][S][ns][12]  3x4 projection K4.T
   size_t off_kinv;                 // float  [B][ns][9]
   size_t off_acc;                  // double [4 + B*S*12] loss sums (pixel, smooth, exp, ssim) + dL/dT
@@ -52,6 +52,7 @@ static inline void sfm_ws_layout(const SfmDesc* d, SfmWsLayout* L) {
     size_t hw = (size_t)(d->H >> s) * (size_t)(d->W >> s);
     L->off_tgt[s] = off;
     off = sfm_align_up(off + (size_t)d->B * hw * 16, 256);
+    off += 256;                      // zero guard texel at element -1: invalid bilinear taps are redirected to it
     L->off_src[s] = off;
     off = sfm_align_up(off + (size_t)d->B * d->S * hw * 16, 256);
   }

@@ -32,8 +32,14 @@ int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, in
 struct SfmFusedParams {
   int B, S, ns;
   int h[SFM_MAX_SCALES], w[SFM_MAX_SCALES];
-  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];
+  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];   // CTA-tile decomposition (SSIM tile kernel)
   int tile_begin[SFM_MAX_SCALES + 1];
+  // warp-task decomposition (marching kernels): a warp owns a 32-column strip x hseg rows of one (snippet, scale)
+  int hseg;
+  int nstrip[SFM_MAX_SCALES], nseg[SFM_MAX_SCALES];
+  int task_begin[SFM_MAX_SCALES + 1];
+  float wm1f[SFM_MAX_SCALES], hm1f[SFM_MAX_SCALES];   // (float)(w-1), (float)(h-1)
+  float hwf[SFM_MAX_SCALES], hhf[SFM_MAX_SCALES];     // (w-1)/2, (h-1)/2
   const float4* tgt_pyr[SFM_MAX_SCALES];
   const float4* src_pyr[SFM_MAX_SCALES];
   const float* disp[SFM_MAX_SCALES];

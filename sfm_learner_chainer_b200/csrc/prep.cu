@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
       const int j = t - n_proj - n_kinv;
       if (j < p.n_acc) p.acc[j] = 0.0;
       if (j == p.n_acc && p.counter) *p.counter = 0u;
+      if (j == p.n_acc && p.do_pyramid)
+        for (int s = 0; s < p.ns; ++s) p.src_pyr[s][-1] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero guard texel
     }
     return;
   }

@@ -55,6 +55,7 @@ SYMBOLS = {
     'sfm_loss_backward': (_i, [_D, _I, _vp, _G, _vp, _vp]),
     'sfm_loss_forward_backward': (_i, [_D, _I, _vp, _G, _vp, _vp]),
     'sfm_scale_grads': (_i, [_D, _vp, _G, _vp]),
+    'sfm_set_kernel_events': (_i, [_vp, _vp]),
     'sfm_pyramid': (_i, [_D, _vp, _vp, _vp, _vp]),
     'sfm_pyramid_export': (_i, [_D, _vp, _i, _vp, _vp, _vp]),
     'sfm_build_tables': (_i, [_D, _vp, _vp, _vp, _vp, _vp]),

@@ -60,7 +60,7 @@ def make_snippets(B, S, H, W, seed=0, n_scales=N_SCALES, harsh=False,
         lo = rs.uniform(-1, 1, shape + (h, w))
         img = 0.9 * _upsample(lo, H, W) + rs.uniform(-0.1, 0.1, shape + (H, W))
         img = np.where(np.abs(img) < 1e-6, 1e-3, img)       # no exact zeros (base_model.py:96)
-        return img.astype(dtype)
+        return np.ascontiguousarray(img, dtype=dtype)      # fancy indexing above leaves a permuted memory order
 
     tgt = image((B, 3))
     src = image((B, S, 3))
@@ -71,15 +71,15 @@ def make_snippets(B, S, H, W, seed=0, n_scales=N_SCALES, harsh=False,
             x = rs.standard_normal((B, 1, h, w))
         else:
             x = _smooth_field(rs, (B, 1), h, w) + 0.05 * rs.standard_normal((B, 1, h, w))
-        disps.append((10.0 / (1.0 + np.exp(-x)) + 0.01).astype(dtype))
-        logits.append(rs.standard_normal((B, S, h, w)).astype(dtype))
+        disps.append(np.ascontiguousarray(10.0 / (1.0 + np.exp(-x)) + 0.01, dtype=dtype))
+        logits.append(np.ascontiguousarray(rs.standard_normal((B, S, h, w)), dtype=dtype))
     if harsh:
         r = rs.uniform(-0.02, 0.02, (B, S, 3))
         t = rs.uniform(-0.05, 0.05, (B, S, 3))
     else:
         r = rs.uniform(-0.01, 0.01, (B, S, 3))
         t = rs.uniform(-0.01, 0.01, (B, S, 3))
-    poses = np.concatenate([r, t], axis=-1).astype(dtype)
+    poses = np.ascontiguousarray(np.concatenate([r, t], axis=-1), dtype=dtype)
     return dict(tgt=tgt, src=src, intrinsics=make_intrinsics(B, H, W, n_scales, dtype),
                 disps=disps, poses=poses, logits=logits)
 
