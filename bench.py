@@ -359,6 +359,7 @@ def run_e2e(cfg_name, steps, device):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    from sfm_learner_chainer_b200.distributed import allreduce_loss_partials
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -381,7 +382,7 @@ def run_b200(args):
 
     def per_step(k):
         if world > 1:
-            pending.append(dist.all_reduce(wl.sets[k % wl.nsets]['losses'][:5], async_op=True))
+            pending.append(allreduce_loss_partials(wl.sets[k % wl.nsets]['losses'][:5], async_op=True))
             if len(pending) > 64:
                 pending.pop(0).wait()
 
@@ -420,9 +421,9 @@ def run_b200(args):
                             parallelism='snippet-sharded x%d, async 5-float loss allreduce' % world if world > 1 else 'single GPU',
                             l2_policy='inputs+outputs rotated over %d buffer sets (%.0f MB > 2 x L2 %.0f MB)' % (
                                 wl.nsets, wl.nsets * wl.A_strict / 1e6, wl.l2_bytes / 1e6),
-                            launch='CUDA graph replay (prep + fused kernel nodes)' if not args.no_graph else 'direct C-ABI calls',
+                            launch='CUDA graph replay (prep + fused + epilogue kernel nodes)' if not args.no_graph else 'direct C-ABI calls',
                             units='target-pyramid pixels = B * sum_s h_s*w_s (%d per step per GPU)' % wl.pix),
-                clocks=clocks, gpu_launches=2 * args.steps)
+                clocks=clocks, gpu_launches=3 * args.steps)
 
     if rank == 0:
         # ---- roofline of the dominant kernel (fused loss), events around the kernel itself

@@ -23,10 +23,10 @@ void sfm_set_error(const char* fmt, ...) {
 
 extern "C" const char* sfm_last_error(void) { return g_err; }
 
-static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+thread_local cudaEvent_t sfm_ev_start = nullptr, sfm_ev_stop = nullptr;   // recorded around the fused kernel (fused_loss.cu)
 extern "C" int sfm_set_kernel_events(void* start_event, void* stop_event) {
-  g_ev_start = (cudaEvent_t)start_event;
-  g_ev_stop = (cudaEvent_t)stop_event;
+  sfm_ev_start = (cudaEvent_t)start_event;
+  sfm_ev_stop = (cudaEvent_t)stop_event;
   return 0;
 }
 extern "C" int sfm_version(void) { return SFM_VERSION; }
@@ -195,10 +195,7 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   if (m.use_ssim) mode |= SFM_MODE_SSIM;
   if (grads) mode |= SFM_MODE_GRAD;
   if (dbg) mode |= SFM_MODE_DEBUG;
-  if (g_ev_start) SFM_CUDA_CHECK(cudaEventRecord(g_ev_start, st));
-  rc = sfm_launch_fused(p, mode, st);
-  if (rc == 0 && g_ev_stop) SFM_CUDA_CHECK(cudaEventRecord(g_ev_stop, st));
-  return rc;
+  return sfm_launch_fused(p, mode, st);
 }
 
 }  // namespace

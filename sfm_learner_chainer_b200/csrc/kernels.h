@@ -23,6 +23,7 @@ struct SfmPrepParams {
   // filled by the launcher
   long long pix_begin[SFM_MAX_SCALES];
   int n_pyr_blocks;
+  int vec0;          // scale 0 copied 4 pixels per thread
 };
 
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
@@ -73,5 +74,6 @@ struct SfmFusedParams {
 // mode bits for the launcher
 enum { SFM_MODE_EXP = 1, SFM_MODE_SSIM = 2, SFM_MODE_GRAD = 4, SFM_MODE_DEBUG = 8 };
 int sfm_launch_fused(SfmFusedParams& p, int mode, cudaStream_t stream);
+extern thread_local cudaEvent_t sfm_ev_start, sfm_ev_stop;   // profiling hook (sfm_set_kernel_events)
 
 int sfm_launch_scale(float* const* ptrs, const long long* counts, int n, const float* gy, cudaStream_t stream);

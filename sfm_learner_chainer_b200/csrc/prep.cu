@@ -56,6 +56,24 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
   const int h = p.H >> s, w = p.W >> s;
   const long long hw = (long long)h * w;
   const long long n_img = (long long)p.B * (1 + p.S);
+  const size_t plane = (size_t)p.H * p.W;
+  if (s == 0 && p.vec0) {
+    // scale 0 is the identity: 4 pixels per thread, 3 x 16-byte planar loads -> 4 x 16-byte texel stores
+    const long long q = hw / 4;
+    if (gid >= n_img * q) return;
+    const int img = (int)(gid / q);
+    const int pix = (int)(gid - (long long)img * q) * 4;
+    const float* base = (img < p.B) ? p.tgt + (size_t)img * 3 * plane : p.src + (size_t)(img - p.B) * 3 * plane;
+    float4* out = (img < p.B) ? p.tgt_pyr[0] + (size_t)img * hw + pix : p.src_pyr[0] + (size_t)(img - p.B) * hw + pix;
+    const float4 r = __ldg(reinterpret_cast<const float4*>(base + pix));
+    const float4 g = __ldg(reinterpret_cast<const float4*>(base + plane + pix));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(base + 2 * plane + pix));
+    out[0] = make_float4(r.x, g.x, bb.x, 0.f);
+    out[1] = make_float4(r.y, g.y, bb.y, 0.f);
+    out[2] = make_float4(r.z, g.z, bb.z, 0.f);
+    out[3] = make_float4(r.w, g.w, bb.w, 0.f);
+    return;
+  }
   if (gid >= n_img * hw) return;
   const int img = (int)(gid / hw);          // [0, B): target b ; [B, B + B*S): source (b, i)
   const int pix = (int)(gid - (long long)img * hw);
@@ -63,13 +81,12 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
   const float* base;
   float4* out;
   if (img < p.B) {
-    base = p.tgt + (size_t)img * 3 * p.H * p.W;
+    base = p.tgt + (size_t)img * 3 * plane;
     out = p.tgt_pyr[s] + (size_t)img * hw + pix;
   } else {
-    base = p.src + (size_t)(img - p.B) * 3 * p.H * p.W;
+    base = p.src + (size_t)(img - p.B) * 3 * plane;
     out = p.src_pyr[s] + (size_t)(img - p.B) * hw + pix;
   }
-  const size_t plane = (size_t)p.H * p.W;
   float4 o;
   o.w = 0.f;
   if (s == 0) {
@@ -121,10 +138,15 @@ __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float*
 
 int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
   SfmPrepParams p = p_in;
+  // vector path for scale 0 needs 16-byte aligned planes and rows
+  p.vec0 = (p.do_pyramid && ((size_t)p.H * p.W) % 4 == 0 && ((uintptr_t)p.tgt & 15) == 0 && ((uintptr_t)p.src & 15) == 0) ? 1 : 0;
   long long total = 0;
   for (int s = 0; s < SFM_MAX_SCALES; ++s) {
     p.pix_begin[s] = total;
-    if (s < p.ns && p.do_pyramid) total += (long long)p.B * (1 + p.S) * (p.H >> s) * (p.W >> s);
+    if (s < p.ns && p.do_pyramid) {
+      const long long n = (long long)p.B * (1 + p.S) * (p.H >> s) * (p.W >> s);
+      total += (s == 0 && p.vec0) ? n / 4 : n;
+    }
   }
   p.n_pyr_blocks = (int)((total + kPrepThreads - 1) / kPrepThreads);
   const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;

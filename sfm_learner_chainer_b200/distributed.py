@@ -1,0 +1,57 @@
+"""Snippet sharding across processes (one process per GPU, torch.distributed for the plumbing).
+
+The loss path shards by snippet b with no data-path collective: every per-pixel quantity
+depends only on (b, scale, source, y, x); the only coupling is that every F.mean divides by the GLOBAL
+batch (base_model.py:109,111,115,184-185).  Each rank therefore runs the fused kernels on its block of
+snippets with `B_global` in the descriptor -- its gradients are final -- and the five reported scalars
+are partial sums that one 5-float allreduce completes.  The reference's analogue is Chainer's
+MultiprocessParallelUpdater (config_utils.py:123-126), which no shipped config enables."""
+
+
+def shard_range(B_global, rank, world_size):
+    """Contiguous block of snippets of `rank`: [lo, hi).  Blocks differ by at most one snippet."""
+    if not (0 <= rank < world_size):
+        raise ValueError('rank %d outside world of %d' % (rank, world_size))
+    base, rem = divmod(B_global, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_arrays(arrays, B_global, rank, world_size):
+    """Slices dict(tgt, src, intrinsics, disps[list], poses, logits[list]) along the snippet axis."""
+    lo, hi = shard_range(B_global, rank, world_size)
+    out = {}
+    for k, v in arrays.items():
+        if v is None:
+            out[k] = None
+        elif isinstance(v, (list, tuple)):
+            out[k] = [x[lo:hi] for x in v]
+        else:
+            out[k] = v[lo:hi]
+    return out
+
+
+def allreduce_loss_partials(losses, group=None, async_op=False):
+    """Sums the 5 loss partials (total, pixel, smooth, exp, ssim) over ranks, in place.
+    `losses`: torch tensor (CUDA with NCCL, CPU with gloo).  Returns the work handle when async."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class ShardedViewSynthesisLoss(object):
+    """ViewSynthesisLoss over this rank's snippet shard; losses are completed by an allreduce."""
+
+    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None):
+        from .functions import ViewSynthesisLoss
+        self.group = group
+        self.op = ViewSynthesisLoss(smooth_reg, exp_reg, ssim_rate, B_global=B_global)
+
+    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, async_op=False):
+        import torch.distributed as dist
+        if self.op.B_global is None and dist.is_initialized():
+            self.op.B_global = int(src.shape[0]) * dist.get_world_size(self.group)
+        losses, grads = self.op.forward_backward(tgt, src, intrinsics, disps, poses, logits)
+        work = allreduce_loss_partials(losses, self.group, async_op=async_op)
+        return losses, grads, work
