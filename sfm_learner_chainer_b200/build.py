@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsfmloss.so')
-SOURCES = ['api.cu', 'prep.cu', 'fused_loss.cu', 'stage.cu']
-HEADERS = ['common.cuh', 'kernels.h', os.path.join(ROOT, 'include', 'sfmloss.h')]
+SOURCES = ['api.cu', 'prep.cu', 'smooth.cu', 'fused_loss.cu', 'stage.cu']
+HEADERS = ['common.cuh', 'kernels.h', 'ssim_march.cuh', os.path.join(ROOT, 'include', 'sfmloss.h')]
 
 
 def _nvcc():

@@ -42,9 +42,10 @@ int sfm_validate_desc(const SfmDesc* d) {
     return SFM_E_INVALID_DESC;
   }
   const int hs = d->H >> (d->n_scales - 1), ws = d->W >> (d->n_scales - 1);
-  if (d->H < 2 || d->W < 2 || hs < 3 || ws < 3) {
-    // resize_images needs >= 2 input rows/cols; the smoothness means need (h-2)*(w-2) > 0 at every scale
-    sfm_set_error("invalid shape: H=%d W=%d give %dx%d at the coarsest of %d scales (need >= 3x3)", d->H, d->W, hs, ws, d->n_scales);
+  if (d->H < 2 || d->W < 2 || hs < 4 || ws < 4) {
+    // resize_images needs >= 2 input rows/cols; the smoothness means need (h-2)*(w-2) > 0 at every scale; and
+    // with >= 4 rows/cols every tap of an out-of-view pixel (x2 rule) lies in the sampler's zero padding
+    sfm_set_error("invalid shape: H=%d W=%d give %dx%d at the coarsest of %d scales (need >= 4x4)", d->H, d->W, hs, ws, d->n_scales);
     return SFM_E_INVALID_SHAPE;
   }
   if ((long long)d->B * (1 + d->S) * d->H * d->W >= (1ll << 31)) {
@@ -267,9 +268,9 @@ extern "C" int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, in
   SfmWsLayout L;
   sfm_ws_layout(desc, &L);
   const char* ws = (const char*)workspace;
-  const int hw = (desc->H >> scale) * (desc->W >> scale);
-  if (tgt_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_tgt[scale]), tgt_out, desc->B, hw, (cudaStream_t)stream))) return rc;
-  if (src_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_src[scale]), src_out, (long long)desc->B * desc->S, hw, (cudaStream_t)stream))) return rc;
+  const int h = desc->H >> scale, w = desc->W >> scale;
+  if (tgt_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_tgt[scale]), tgt_out, desc->B, h, w, 0, (cudaStream_t)stream))) return rc;
+  if (src_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_src[scale]), src_out, (long long)desc->B * desc->S, h, w, 1, (cudaStream_t)stream))) return rc;
   return 0;
 }
 

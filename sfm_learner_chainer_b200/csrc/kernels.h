@@ -27,7 +27,7 @@ struct SfmPrepParams {
 };
 
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
-int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int hw, cudaStream_t stream);
+int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int h, int w, int padded, cudaStream_t stream);
 
 // Fused loss kernel parameters (one launch covers every scale, source and snippet).
 struct SfmFusedParams {
@@ -74,6 +74,7 @@ struct SfmFusedParams {
 // mode bits for the launcher
 enum { SFM_MODE_EXP = 1, SFM_MODE_SSIM = 2, SFM_MODE_GRAD = 4, SFM_MODE_DEBUG = 8 };
 int sfm_launch_fused(SfmFusedParams& p, int mode, cudaStream_t stream);
+int sfm_launch_smooth(SfmFusedParams& p, int grad, cudaStream_t stream);   // smooth.cu
 extern thread_local cudaEvent_t sfm_ev_start, sfm_ev_stop;   // profiling hook (sfm_set_kernel_events)
 
 int sfm_launch_scale(float* const* ptrs, const long long* counts, int n, const float* gy, cudaStream_t stream);

@@ -36,11 +36,25 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
       sfm_inv3(K, inv);
       for (int k = 0; k < 9; ++k) p.kinv_out[(size_t)j * 9 + k] = inv[k];
     } else {
-      const int j = t - n_proj - n_kinv;
-      if (j < p.n_acc) p.acc[j] = 0.0;
-      if (j == p.n_acc && p.counter) *p.counter = 0u;
-      if (j == p.n_acc && p.do_pyramid)
-        for (int s = 0; s < p.ns; ++s) p.src_pyr[s][-1] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero guard texel
+      long long j = (long long)t - n_proj - n_kinv;
+      if (j < p.n_acc) { p.acc[j] = 0.0; return; }
+      j -= p.n_acc;
+      if (j == 0 && p.counter) *p.counter = 0u;
+      if (!p.do_pyramid) return;
+      // zero padding of the source pyramid: column w of every row, and the two rows below every image
+      for (int s = 0; s < p.ns; ++s) {
+        const int h = p.H >> s, w = p.W >> s, pitch = sfm_src_pitch(w);
+        const long long per_img = (long long)h + 2ll * pitch;
+        const long long n = (long long)p.B * p.S * per_img;
+        if (j < n) {
+          const long long img = j / per_img;
+          const int k = (int)(j - img * per_img);
+          const long long off = (k < h) ? (long long)k * pitch + w : (long long)h * pitch + (k - h);
+          p.src_pyr[s][img * ((long long)sfm_src_rows(h) * pitch) + off] = make_float4(0.f, 0.f, 0.f, 0.f);
+          return;
+        }
+        j -= n;
+      }
     }
     return;
   }
@@ -64,7 +78,13 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
     const int img = (int)(gid / q);
     const int pix = (int)(gid - (long long)img * q) * 4;
     const float* base = (img < p.B) ? p.tgt + (size_t)img * 3 * plane : p.src + (size_t)(img - p.B) * 3 * plane;
-    float4* out = (img < p.B) ? p.tgt_pyr[0] + (size_t)img * hw + pix : p.src_pyr[0] + (size_t)(img - p.B) * hw + pix;
+    float4* out;
+    if (img < p.B) {
+      out = p.tgt_pyr[0] + (size_t)img * hw + pix;
+    } else {
+      const int yy = pix / w, xx = pix - yy * w;          // w % 4 == 0: the 4 pixels share a row
+      out = p.src_pyr[0] + (size_t)(img - p.B) * sfm_src_rows(h) * sfm_src_pitch(w) + (size_t)yy * sfm_src_pitch(w) + xx;
+    }
     const float4 r = __ldg(reinterpret_cast<const float4*>(base + pix));
     const float4 g = __ldg(reinterpret_cast<const float4*>(base + plane + pix));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(base + 2 * plane + pix));
@@ -85,7 +105,7 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
     out = p.tgt_pyr[s] + (size_t)img * hw + pix;
   } else {
     base = p.src + (size_t)(img - p.B) * 3 * plane;
-    out = p.src_pyr[s] + (size_t)(img - p.B) * hw + pix;
+    out = p.src_pyr[s] + (size_t)(img - p.B) * sfm_src_rows(h) * sfm_src_pitch(w) + (size_t)y * sfm_src_pitch(w) + x;
   }
   float4 o;
   o.w = 0.f;
@@ -122,12 +142,14 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
 }
 
 __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float* __restrict__ out, long long n_img,
-                                          int hw) {
+                                          int h, int w, int pitch, int rows) {
+  const int hw = h * w;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_img * hw) return;
   const long long img = gid / hw;
   const int pix = (int)(gid - img * hw);
-  const float4 v = pyr[gid];
+  const int y = pix / w, x = pix - y * w;
+  const float4 v = pyr[img * ((long long)rows * pitch) + (long long)y * pitch + x];
   float* o = out + (size_t)img * 3 * hw + pix;
   o[0] = v.x;
   o[hw] = v.y;
@@ -139,7 +161,7 @@ __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float*
 int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
   SfmPrepParams p = p_in;
   // vector path for scale 0 needs 16-byte aligned planes and rows
-  p.vec0 = (p.do_pyramid && ((size_t)p.H * p.W) % 4 == 0 && ((uintptr_t)p.tgt & 15) == 0 && ((uintptr_t)p.src & 15) == 0) ? 1 : 0;
+  p.vec0 = (p.do_pyramid && p.W % 4 == 0 && ((uintptr_t)p.tgt & 15) == 0 && ((uintptr_t)p.src & 15) == 0) ? 1 : 0;
   long long total = 0;
   for (int s = 0; s < SFM_MAX_SCALES; ++s) {
     p.pix_begin[s] = total;
@@ -149,17 +171,22 @@ int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
     }
   }
   p.n_pyr_blocks = (int)((total + kPrepThreads - 1) / kPrepThreads);
-  const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;
+  long long n_pad = 0;
+  if (p.do_pyramid)
+    for (int s = 0; s < p.ns; ++s) n_pad += (long long)p.B * p.S * ((p.H >> s) + 2ll * sfm_src_pitch(p.W >> s));
+  const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1 + n_pad;
   const int tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
   sfm_prep_kernel<<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
   SFM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int hw, cudaStream_t stream) {
-  const long long n = n_img * hw;
+int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int h, int w, int padded,
+                              cudaStream_t stream) {
+  const long long n = n_img * h * w;
   if (n == 0) return 0;
-  sfm_pyramid_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pyr, out, n_img, hw);
+  sfm_pyramid_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pyr, out, n_img, h, w, padded ? sfm_src_pitch(w) : w,
+                                                                           padded ? sfm_src_rows(h) : h);
   SFM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
