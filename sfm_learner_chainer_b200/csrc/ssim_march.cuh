@@ -1,5 +1,345 @@
-// ssim_march.cuh -- placeholder
-int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug, long long want_warps, cudaStream_t stream) {
-  sfm_set_error("SSIM kernel not built yet");
-  return SFM_E_UNSUPPORTED;
+// ssim_march.cuh -- SSIM marching kernel: L1 + SSIM photometric terms (base_model.py:110-115, 126-142),
+// forward and backward in one march.  Included by fused_loss.cu (shares its projection / blend helpers).
+//
+// A warp owns a strip of 28 interior columns (+2 halo columns each side = 32 lanes) x hseg rows and
+// marches down rows y0-2 .. y1+1, lane = column.  Per row r:
+//   stage A  warp the pixel (r, lane): projection, 4-tap gather, blend, image gradients dP/du, dP/dv
+//   stage B  horizontal 3-sums of P, P^2, P.T, T, T^2 (neighbours through warp shuffles)
+//   stage C  vertical 3-sums (register ring over the last three rows) -> SSIM at (r-1, lane), its loss
+//            and the three gradient fields g_a, g_s, g_c
+//   stage D  horizontal 3-sums of the gradient fields
+//   stage E  vertical 3-sums -> dL/dP at (r-2, lane) = A(g_a) + 2P.A(g_s) + T.A(g_c) + L1 part
+//   stage F  sampler / projection backward of pixel (r-2, lane) from its forward record
+// The rings and the two-row delay line of forward records live in registers; the row loop is unrolled
+// three times so that the ring rotation is pure renaming.  No shared memory, no barrier; the only
+// atomics are the per-task flush.  dL/dP accumulates as sum gq, sum gq*depth, sum gq*depth*y per lane
+// (the lane's column x is constant along the march) and is expanded with Kinv before the flush.
+#pragma once
+
+namespace {
+
+constexpr int SSIM_IW = 28;     // interior columns per strip
+
+struct StripTask {
+  int s, b, x0, y0, y1;
+};
+
+__device__ __forceinline__ StripTask decode_strip(const SfmFusedParams& p, int t) {
+  StripTask k;
+  int s = 0;
+#pragma unroll
+  for (int q = 1; q < SFM_MAX_SCALES; ++q)
+    if (q < p.ns && t >= p.task_begin[q]) s = q;
+  t -= p.task_begin[s];
+  k.s = s;
+  const int seg = t % p.nseg[s];
+  t /= p.nseg[s];
+  const int strip = t % p.nstrip[s];
+  k.b = t / p.nstrip[s];
+  k.x0 = strip * SSIM_IW;
+  k.y0 = seg * p.hseg;
+  k.y1 = min(k.y0 + p.hseg, p.h[s]);
+  return k;
+}
+
+// forward record of one pixel, kept for two rows until its backward runs
+struct Rec {
+  float Ix[3], Iy[3];     // dP_c/du, dP_c/dv (pixel units)
+  float P[3], T[3];
+  float q0, q1, q2, r;    // projection, 1/z (0 when out of view)
+  float depth;
+};
+
+template <int N>
+struct IC { static constexpr int value = N; };
+
+#ifndef SFM_MINB_SSIM
+#define SFM_MINB_SSIM 10
+#endif
+template <bool GRAD, bool ACCUM, bool DEBUG>
+__global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
+  const int lane = threadIdx.x;
+  const StripTask t = decode_strip(p, blockIdx.x);
+  const int s = t.s, b = t.b, h = p.h[s], w = p.w[s], S = p.S;
+  const Geo geo = make_geo(p, s);
+  const int xx = t.x0 - 2 + lane;                       // this lane's image column (may be outside)
+  const bool col_in = (xx >= 0) && (xx < w);
+  const bool col_own = (lane >= 2) && (lane < 2 + SSIM_IW) && (xx < w);
+  const float gyv = p.gy ? __ldg(p.gy) : 1.f;
+  const float inv_n3 = p.inv_n3[s];
+  const float wpix = gyv * (1.f - p.ssim_rate) * inv_n3;
+  const float wssim = gyv * p.ssim_rate * inv_n3;
+  const float c1v = 0.01f * 0.01f, c2v = 0.03f * 0.03f, k9 = 1.f / 9.f;
+  const float* __restrict__ kinvp = p.kinv + ((size_t)b * p.ns + s) * 9;
+  const float xf = (float)xx;
+  const float kk0 = __ldg(kinvp + 0), kk1 = __ldg(kinvp + 1), kk2 = __ldg(kinvp + 2);
+  const float kk3 = __ldg(kinvp + 3), kk4 = __ldg(kinvp + 4), kk5 = __ldg(kinvp + 5);
+  const float kk6 = __ldg(kinvp + 6), kk7 = __ldg(kinvp + 7), kk8 = __ldg(kinvp + 8);
+  // ray = Kinv.(x, y, 1): r_k = (k_k0*x + k_k1*y) + k_k2 ; the x products are row invariant
+  const float rxx = __fmul_rn(kk0, xf), ryx = __fmul_rn(kk3, xf), rzx = __fmul_rn(kk6, xf);
+  const int plane = h * w;
+  const float* __restrict__ disp = p.disp[s] + (size_t)b * plane;
+  const float4* __restrict__ tgt = p.tgt_pyr[s] + (size_t)b * plane;
+  float* __restrict__ gdisp = GRAD ? p.gdisp[s] + (size_t)b * plane : nullptr;
+  const size_t src_img = (size_t)sfm_src_rows(h) * geo.pitch;
+  float pix_part = 0.f, ssim_part = 0.f;
+  const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end)
+
+  for (int i = 0; i < S; ++i) {
+    float P[12];
+    {
+      const float* __restrict__ pp = p.proj + (((size_t)b * S + i) * p.ns + s) * 12;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = __ldg(pp + k);
+    }
+    float accA[3] = {0.f, 0.f, 0.f}, accB[3] = {0.f, 0.f, 0.f}, accC[3] = {0.f, 0.f, 0.f};
+    const bool first = (i == 0);
+    const float4* __restrict__ img = p.src_pyr[s] + ((size_t)b * S + i) * src_img;
+    // rings: window row sums (P, P^2, P.T, T, T^2 per channel), gradient-field row sums, forward records
+    float hs[3][15], gs[3][9];
+    Rec rec[3];
+    bool mask[3];                                        // all-zero mask of the row's pixel (base_model.py:96)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int q = 0; q < 15; ++q) hs[k][q] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) gs[k][q] = 0.f;
+      mask[k] = true;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rec[k].Ix[c] = rec[k].Iy[c] = rec[k].P[c] = rec[k].T[c] = 0.f;
+      rec[k].q0 = rec[k].q1 = rec[k].q2 = rec[k].r = rec[k].depth = 0.f;
+    }
+    auto load_dT = [&](int r, float& dd, float4& TT) {
+      dd = 1.f;
+      TT = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_in && (r >= 0) && (r < h) && (r < r_end)) {
+        dd = __ldg(disp + r * w + xx);
+        TT = __ldg(tgt + r * w + xx);
+      }
+    };
+    float dA, dB;            // disparity / target of rows r, r+1 (fetched ahead)
+    float4 TA, TB;
+    load_dT(r_begin, dA, TA);
+    load_dT(r_begin + 1, dB, TB);
+
+    auto step = [&](auto PH, const int r) {
+      constexpr int cur = decltype(PH)::value, pv1 = (cur + 2) % 3, pv2 = (cur + 1) % 3;
+      // ---------------- early loads: the row two ahead, the partial gdisp of the row whose backward runs now
+      float dC;
+      float4 TC;
+      load_dT(r + 2, dC, TC);
+      const int rf = r - 2;
+      const bool do_f = col_own && rf >= t.y0 && rf < t.y1;
+      float g_old = 0.f;
+      if (GRAD && (ACCUM || !first) && do_f) g_old = gdisp[rf * w + xx];
+      // ---------------- stage A: warp pixel (r, lane)
+      const bool in_img = col_in && (r >= 0) && (r < h);
+      Rec& rc_ = rec[cur];
+      {
+        const float d = dA;
+        const float4 T = TA;
+        const float depth = rcp_newton(d);
+        const float yf = (float)r;
+        const float rx = __fadd_rn(__fadd_rn(rxx, __fmul_rn(kk1, yf)), kk2);
+        const float ry = __fadd_rn(__fadd_rn(ryx, __fmul_rn(kk4, yf)), kk5);
+        const float rz = __fadd_rn(__fadd_rn(rzx, __fmul_rn(kk7, yf)), kk8);
+        const float X = __fmul_rn(depth, rx), Y = __fmul_rn(depth, ry), Z = __fmul_rn(depth, rz);
+        PairFwd f;
+        pair_project(P, X, Y, Z, geo, f, in_img);
+        const float4* __restrict__ tp = img + f.idx;
+        const float4 I00 = __ldg(tp), I01 = __ldg(tp + 1), I10 = __ldg(tp + geo.pitch), I11 = __ldg(tp + geo.pitch + 1);
+        float P0, P1, P2;
+        pair_blend(f, I00, I01, I10, I11, P0, P1, P2);
+        const bool m = (P0 == 0.f) && (P1 == 0.f) && (P2 == 0.f);               // true outside the image / view
+        const bool own = col_own && (r >= t.y0) && (r < t.y1);
+        pix_part += (own && !m) ? (fabsf(P0 - T.x) + fabsf(P1 - T.y) + fabsf(P2 - T.z)) : 0.f;
+        mask[cur] = m;
+        rc_.P[0] = P0; rc_.P[1] = P1; rc_.P[2] = P2;
+        rc_.T[0] = T.x; rc_.T[1] = T.y; rc_.T[2] = T.z;
+        if (GRAD) {
+          rc_.Ix[0] = f.wc * (I01.x - I00.x) + f.wd * (I11.x - I10.x);
+          rc_.Ix[1] = f.wc * (I01.y - I00.y) + f.wd * (I11.y - I10.y);
+          rc_.Ix[2] = f.wc * (I01.z - I00.z) + f.wd * (I11.z - I10.z);
+          rc_.Iy[0] = f.wa * (I10.x - I00.x) + f.wb * (I11.x - I01.x);
+          rc_.Iy[1] = f.wa * (I10.y - I00.y) + f.wb * (I11.y - I01.y);
+          rc_.Iy[2] = f.wa * (I10.z - I00.z) + f.wb * (I11.z - I01.z);
+          rc_.q0 = f.q0; rc_.q1 = f.q1; rc_.q2 = f.q2; rc_.r = f.r;
+          rc_.depth = depth;
+        }
+        if (DEBUG && own) {
+          const size_t im = (size_t)b * S + i;
+          const size_t pix = (size_t)r * w + xx;
+          debug_dump(p, s, im * plane + pix, im * 3 * plane + pix, plane, P, X, Y, Z, w, h, geo, f, P0, P1, P2);
+        }
+      }
+      dA = dB; TA = TB;
+      dB = dC; TB = TC;
+      // ---------------- stage B: row sums of P, P^2, P.T, T, T^2 over lanes-1..+1 (zero outside the image)
+      {
+        float* h0 = hs[cur];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float pv = rc_.P[c], tv = rc_.T[c];
+          const float pl = __shfl_up_sync(0xffffffffu, pv, 1), pr = __shfl_down_sync(0xffffffffu, pv, 1);
+          const float tl = __shfl_up_sync(0xffffffffu, tv, 1), tr = __shfl_down_sync(0xffffffffu, tv, 1);
+          h0[c * 5 + 0] = (pl + pv) + pr;
+          h0[c * 5 + 1] = fmaf(pr, pr, fmaf(pv, pv, pl * pl));
+          h0[c * 5 + 2] = fmaf(pr, tr, fmaf(pv, tv, pl * tl));
+          h0[c * 5 + 3] = (tl + tv) + tr;
+          h0[c * 5 + 4] = fmaf(tr, tr, fmaf(tv, tv, tl * tl));
+        }
+      }
+      // ---------------- stage C: SSIM at (rc = r-1, lane) from rows r-2, r-1, r
+      const int rc = r - 1;
+      float g0[9];
+      {
+        const float* h0 = hs[cur];
+        const float* h1 = hs[pv1];
+        const float* h2 = hs[pv2];
+        const bool c_in = col_in && (rc >= 0) && (rc < h) && (r >= r_begin + 2);
+        const bool live_px = c_in && !mask[pv1];
+        const bool own_c = col_own && (rc >= t.y0) && (rc < t.y1);
+        const float lw = (live_px && own_c) ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float a = ((h2[c * 5 + 0] + h1[c * 5 + 0]) + h0[c * 5 + 0]) * k9;
+          const float s2 = ((h2[c * 5 + 1] + h1[c * 5 + 1]) + h0[c * 5 + 1]) * k9;
+          const float cc = ((h2[c * 5 + 2] + h1[c * 5 + 2]) + h0[c * 5 + 2]) * k9;
+          const float my = ((h2[c * 5 + 3] + h1[c * 5 + 3]) + h0[c * 5 + 3]) * k9;
+          const float tt = ((h2[c * 5 + 4] + h1[c * 5 + 4]) + h0[c * 5 + 4]) * k9;
+          const float aa = a * a, mm = my * my, am = a * my;
+          const float sx = s2 - aa, sy = tt - mm, sxy = cc - am;
+          const float n1 = fmaf(2.f, am, c1v), n2 = fmaf(2.f, sxy, c2v);
+          const float d1v = (aa + mm) + c1v, d2v = (sx + sy) + c2v;
+          const float n = n1 * n2, dd = d1v * d2v;
+          const float rd = rcp_approx(dd);
+          const float q = n * rd;
+          const float raw = fmaf(-0.5f, q, 0.5f);
+          ssim_part = fmaf(__saturatef(raw), lw, ssim_part);
+          if (GRAD) {
+            const bool live = live_px && (raw >= 0.f) && (raw <= 1.f);     // F.clip passes gradient inside [0, 1]
+            const float g_n = live ? (-0.5f * wssim) * rd : 0.f;
+            const float g_d = -g_n * q;
+            g0[c * 3 + 0] = fmaf(g_n * my, n2 - n1, (g_d * a) * (d2v - d1v));   // g_a / 2
+            g0[c * 3 + 1] = g_d * d1v;                                           // g_s
+            g0[c * 3 + 2] = g_n * n1;                                            // g_c / 2
+          }
+        }
+      }
+      if (GRAD) {
+        // ---------------- stage D: row sums of the three gradient fields of row rc
+        float* gh0 = gs[cur];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const float gl = __shfl_up_sync(0xffffffffu, g0[q], 1), grt = __shfl_down_sync(0xffffffffu, g0[q], 1);
+          gh0[q] = (gl + g0[q]) + grt;
+        }
+        // ---------------- stages E + F: dL/dP and the warp backward for pixel (rf = r-2, lane)
+        const float* g1 = gs[pv1];
+        const float* g2 = gs[pv2];
+        const Rec& rb = rec[pv2];
+        const bool mf = mask[pv2];
+        float gP[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float Aa = (g2[c * 3 + 0] + g1[c * 3 + 0]) + gh0[c * 3 + 0];
+          const float As = (g2[c * 3 + 1] + g1[c * 3 + 1]) + gh0[c * 3 + 1];
+          const float Ac = (g2[c * 3 + 2] + g1[c * 3 + 2]) + gh0[c * 3 + 2];
+          // dL/dP = A(g_a) + 2P.A(g_s) + T.A(g_c), A = 3x3 mean; g_a, g_c carry a factor 1/2
+          const float gsv = (2.f * k9) * fmaf(rb.T[c], Ac, fmaf(rb.P[c], As, Aa));
+          gP[c] = gsv + ((mf || !do_f) ? 0.f : sign_times(rb.P[c] - rb.T[c], wpix));
+          gP[c] = do_f ? gP[c] : 0.f;
+        }
+        // sampler + projection backward; out-of-view pixels have Ix = Iy = 0 and r = 0
+        const float gu = gP[0] * rb.Ix[0] + gP[1] * rb.Ix[1] + gP[2] * rb.Ix[2];
+        const float gv = gP[0] * rb.Iy[0] + gP[1] * rb.Iy[1] + gP[2] * rb.Iy[2];
+        const float gq0 = gu * rb.r, gq1 = gv * rb.r;
+        const float gq2 = -(gq0 * rb.q0 + gq1 * rb.q1) * rb.r;
+        const float gdd = gq0 * (rb.q0 - P[3]) + gq1 * (rb.q1 - P[7]) + gq2 * (rb.q2 - P[11]);
+        const float yfb = (float)rf;
+        const float e0 = gq0 * rb.depth, e1 = gq1 * rb.depth, e2 = gq2 * rb.depth;
+        accA[0] += e0; accA[1] += e1; accA[2] += e2;
+        accB[0] = fmaf(e0, yfb, accB[0]); accB[1] = fmaf(e1, yfb, accB[1]); accB[2] = fmaf(e2, yfb, accB[2]);
+        accC[0] += gq0; accC[1] += gq1; accC[2] += gq2;
+        if (do_f) gdisp[rf * w + xx] = g_old - gdd * rb.depth;
+      }
+    };
+
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; r += 3) {
+      step(IC<0>{}, r);
+      if (r + 1 < r_end) step(IC<1>{}, r + 1);
+      if (r + 2 < r_end) step(IC<2>{}, r + 2);
+    }
+    // ---- flush: expand (A, B, C) to dL/dP = sum gq (x) (X, Y, Z, 1) with X = depth*((k0 x + k2) + k1 y) ...
+    const bool last = (i == S - 1);
+    if (GRAD || last) {
+      float acc[12];
+      if (GRAD) {
+        const float cx = rxx + kk2, cy = ryx + kk5, cz = rzx + kk8;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          acc[k * 4 + 0] = cx * accA[k] + kk1 * accB[k];
+          acc[k * 4 + 1] = cy * accA[k] + kk4 * accB[k];
+          acc[k * 4 + 2] = cz * accA[k] + kk7 * accB[k];
+          acc[k * 4 + 3] = accC[k];
+        }
+      }
+      flush_dP(p, acc, b, i, s, lane, last ? pix_part * inv_n3 : 0.f, last ? ssim_part * inv_n3 : 0.f, 0.f, 0, 3, -1, GRAD);
+    }
+  }
+}
+
+}  // namespace
+
+template <typename K>
+static int launch_ssim_kernel(K kernel, const SfmFusedParams& p, cudaStream_t stream) {
+  const int n_tasks = p.task_begin[SFM_MAX_SCALES];
+  if (sfm_ev_start) SFM_CUDA_CHECK(cudaEventRecord(sfm_ev_start, stream));
+  kernel<<<n_tasks, 32, 0, stream>>>(p);
+  SFM_CUDA_CHECK(cudaGetLastError());
+  if (sfm_ev_stop) SFM_CUDA_CHECK(cudaEventRecord(sfm_ev_stop, stream));
+  return 0;
+}
+
+int launch_epilogue(const SfmFusedParams& p, cudaStream_t stream);
+
+static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug, long long want_warps, cudaStream_t stream) {
+  int hseg = 64;
+  for (;;) {
+    long long n = 0;
+    for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + hseg - 1) / hseg);
+    if (n >= want_warps || hseg <= 8) break;
+    hseg >>= 1;
+  }
+  {
+    const char* e = getenv("SFM_HSEG");          // development knob
+    if (e && atoi(e) > 0) hseg = atoi(e);
+  }
+  p.hseg = hseg;
+  int total = 0;
+  for (int s = 0; s < SFM_MAX_SCALES; ++s) {
+    p.task_begin[s] = total;
+    if (s < p.ns) {
+      p.nstrip[s] = (p.w[s] + SSIM_IW - 1) / SSIM_IW;
+      p.nseg[s] = (p.h[s] + hseg - 1) / hseg;
+      total += p.B * p.nstrip[s] * p.nseg[s];
+    } else {
+      p.nstrip[s] = p.nseg[s] = 1;
+    }
+  }
+  p.task_begin[SFM_MAX_SCALES] = total;
+  int rc;
+  if (grad) {
+    if (accum) rc = debug ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, true>, p, stream)
+                          : launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false>, p, stream);
+    else rc = debug ? launch_ssim_kernel(sfm_ssim_march_kernel<true, false, true>, p, stream)
+                    : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false>, p, stream);
+  } else {
+    rc = debug ? launch_ssim_kernel(sfm_ssim_march_kernel<false, false, true>, p, stream)
+               : launch_ssim_kernel(sfm_ssim_march_kernel<false, false, false>, p, stream);
+  }
+  if (rc) return rc;
+  return launch_epilogue(p, stream);
 }
