@@ -8,11 +8,18 @@
 namespace {
 
 constexpr int kPrepThreads = 256;
+constexpr int kBand = 8;          // full-resolution rows per pyramid CTA
 
-// One thread = one output pixel of one image at one scale.
+// Pyramid CTA = (image, band of kBand full-resolution rows).  It copies the band to scale 0 and produces
+// every coarser-scale row whose top tap row v0 lies in the band, so the full-resolution planes are read
+// from HBM once (the coarser scales re-read them through L1/L2 while they are hot) instead of once per
+// scale.  One texel per thread and iteration, lanes along x: 4-byte planar loads and 16-byte texel stores
+// are fully coalesced.
 // Coordinates follow Chainer's resize_images: u = linspace(0, W-1, w_s) in float64 (x*step, last
 // element pinned to W-1), u0 = clip(floor(u), 0, W-2), weights are float64 products cast to fp32,
 // y = ((w1*a + w2*b) + w3*c) + w4*d in fp32.  Scale 0 is the identity and is copied.
+// Source images carry the zero border of the padded layout (common.cuh): column w of every row and the
+// two rows below the image.
 __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_constant__ SfmPrepParams p) {
   const int blk = blockIdx.x;
   if (blk >= p.n_pyr_blocks) {
@@ -36,109 +43,71 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
       sfm_inv3(K, inv);
       for (int k = 0; k < 9; ++k) p.kinv_out[(size_t)j * 9 + k] = inv[k];
     } else {
-      long long j = (long long)t - n_proj - n_kinv;
-      if (j < p.n_acc) { p.acc[j] = 0.0; return; }
-      j -= p.n_acc;
-      if (j == 0 && p.counter) *p.counter = 0u;
-      if (!p.do_pyramid) return;
-      // zero padding of the source pyramid: column w of every row, and the two rows below every image
-      for (int s = 0; s < p.ns; ++s) {
-        const int h = p.H >> s, w = p.W >> s, pitch = sfm_src_pitch(w);
-        const long long per_img = (long long)h + 2ll * pitch;
-        const long long n = (long long)p.B * p.S * per_img;
-        if (j < n) {
-          const long long img = j / per_img;
-          const int k = (int)(j - img * per_img);
-          const long long off = (k < h) ? (long long)k * pitch + w : (long long)h * pitch + (k - h);
-          p.src_pyr[s][img * ((long long)sfm_src_rows(h) * pitch) + off] = make_float4(0.f, 0.f, 0.f, 0.f);
-          return;
-        }
-        j -= n;
-      }
+      const int j = t - n_proj - n_kinv;
+      if (j < p.n_acc) p.acc[j] = 0.0;
+      if (j == p.n_acc && p.counter) *p.counter = 0u;
     }
     return;
   }
-  if (!p.do_pyramid) return;
 
   // ---- pyramid
-  long long gid = (long long)blk * kPrepThreads + threadIdx.x;
-  int s = 0;
-#pragma unroll
-  for (int k = 1; k < SFM_MAX_SCALES; ++k)
-    if (k < p.ns && gid >= p.pix_begin[k]) s = k;
-  gid -= p.pix_begin[s];
-  const int h = p.H >> s, w = p.W >> s;
-  const long long hw = (long long)h * w;
-  const long long n_img = (long long)p.B * (1 + p.S);
-  const size_t plane = (size_t)p.H * p.W;
-  if (s == 0 && p.vec0) {
-    // scale 0 is the identity: 4 pixels per thread, 3 x 16-byte planar loads -> 4 x 16-byte texel stores
-    const long long q = hw / 4;
-    if (gid >= n_img * q) return;
-    const int img = (int)(gid / q);
-    const int pix = (int)(gid - (long long)img * q) * 4;
-    const float* base = (img < p.B) ? p.tgt + (size_t)img * 3 * plane : p.src + (size_t)(img - p.B) * 3 * plane;
-    float4* out;
-    if (img < p.B) {
-      out = p.tgt_pyr[0] + (size_t)img * hw + pix;
+  const int n_bands = (p.H + kBand - 1) / kBand;
+  const int img = blk / n_bands;            // [0, B): target b ; [B, B + B*S): source (b, i)
+  const int band = blk - img * n_bands;
+  const int Y0 = band * kBand, Y1 = min(Y0 + kBand, p.H);
+  const bool is_src = img >= p.B;
+  const int H = p.H, W = p.W;
+  const size_t plane = (size_t)H * W;
+  const float* __restrict__ base = is_src ? p.src + (size_t)(img - p.B) * 3 * plane : p.tgt + (size_t)img * 3 * plane;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < p.ns; ++s) {
+    const int h = H >> s, w = W >> s;
+    const int pitch = is_src ? sfm_src_pitch(w) : w;
+    float4* __restrict__ out = is_src ? p.src_pyr[s] + (size_t)(img - p.B) * sfm_src_rows(h) * pitch
+                                      : p.tgt_pyr[s] + (size_t)img * h * w;
+    if (s == 0) {
+      for (int y = Y0 + warp; y < Y1; y += kPrepThreads / 32) {
+        const float* __restrict__ row = base + (size_t)y * W;
+        float4* __restrict__ orow = out + (size_t)y * pitch;
+        for (int x = lane; x < W; x += 32)
+          orow[x] = make_float4(__ldg(row + x), __ldg(row + plane + x), __ldg(row + 2 * plane + x), 0.f);
+        if (is_src && lane == 0) orow[W] = zero4;
+      }
     } else {
-      const int yy = pix / w, xx = pix - yy * w;          // w % 4 == 0: the 4 pixels share a row
-      out = p.src_pyr[0] + (size_t)(img - p.B) * sfm_src_rows(h) * sfm_src_pitch(w) + (size_t)yy * sfm_src_pitch(w) + xx;
-    }
-    const float4 r = __ldg(reinterpret_cast<const float4*>(base + pix));
-    const float4 g = __ldg(reinterpret_cast<const float4*>(base + plane + pix));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(base + 2 * plane + pix));
-    out[0] = make_float4(r.x, g.x, bb.x, 0.f);
-    out[1] = make_float4(r.y, g.y, bb.y, 0.f);
-    out[2] = make_float4(r.z, g.z, bb.z, 0.f);
-    out[3] = make_float4(r.w, g.w, bb.w, 0.f);
-    return;
-  }
-  if (gid >= n_img * hw) return;
-  const int img = (int)(gid / hw);          // [0, B): target b ; [B, B + B*S): source (b, i)
-  const int pix = (int)(gid - (long long)img * hw);
-  const int y = pix / w, x = pix - y * w;
-  const float* base;
-  float4* out;
-  if (img < p.B) {
-    base = p.tgt + (size_t)img * 3 * plane;
-    out = p.tgt_pyr[s] + (size_t)img * hw + pix;
-  } else {
-    base = p.src + (size_t)(img - p.B) * 3 * plane;
-    out = p.src_pyr[s] + (size_t)(img - p.B) * sfm_src_rows(h) * sfm_src_pitch(w) + (size_t)y * sfm_src_pitch(w) + x;
-  }
-  float4 o;
-  o.w = 0.f;
-  if (s == 0) {
-    const size_t a = (size_t)y * p.W + x;
-    o.x = __ldg(base + a);
-    o.y = __ldg(base + plane + a);
-    o.z = __ldg(base + 2 * plane + a);
-  } else {
-    const double stepx = (w > 1) ? __ddiv_rn((double)(p.W - 1), (double)(w - 1)) : 0.0;
-    const double stepy = (h > 1) ? __ddiv_rn((double)(p.H - 1), (double)(h - 1)) : 0.0;
-    const double u = (x == w - 1 && w > 1) ? (double)(p.W - 1) : __dmul_rn((double)x, stepx);
-    const double v = (y == h - 1 && h > 1) ? (double)(p.H - 1) : __dmul_rn((double)y, stepy);
-    int u0 = (int)floor(u), v0 = (int)floor(v);
-    u0 = min(max(u0, 0), p.W - 2);
-    v0 = min(max(v0, 0), p.H - 2);
-    const double ua = __dsub_rn((double)(u0 + 1), u), ub = __dsub_rn(u, (double)u0);
-    const double va = __dsub_rn((double)(v0 + 1), v), vb = __dsub_rn(v, (double)v0);
-    const float w1 = (float)__dmul_rn(ua, va), w2 = (float)__dmul_rn(ub, va);
-    const float w3 = (float)__dmul_rn(ua, vb), w4 = (float)__dmul_rn(ub, vb);
-    const size_t a00 = (size_t)v0 * p.W + u0;
-    const size_t a10 = a00 + p.W;
-    float r[3];
+      const double stepx = (w > 1) ? __ddiv_rn((double)(W - 1), (double)(w - 1)) : 0.0;
+      const double stepy = (h > 1) ? __ddiv_rn((double)(H - 1), (double)(h - 1)) : 0.0;
+      // candidate rows: those whose v0 can fall in [Y0, Y1); the exact test is below
+      const int y_lo = (stepy > 0.0) ? max(0, (int)((double)Y0 / stepy) - 1) : 0;
+      const int y_hi = (stepy > 0.0) ? min(h, (int)((double)Y1 / stepy) + 2) : h;
+      for (int y = y_lo + warp; y < y_hi; y += kPrepThreads / 32) {
+        const double v = (y == h - 1 && h > 1) ? (double)(H - 1) : __dmul_rn((double)y, stepy);
+        const int v0 = min(max((int)floor(v), 0), H - 2);
+        if (v0 < Y0 || v0 >= Y1) continue;          // another band owns this row (warp-uniform)
+        const double va = __dsub_rn((double)(v0 + 1), v), vb = __dsub_rn(v, (double)v0);
+        const float* __restrict__ r0 = base + (size_t)v0 * W;
+        float4* __restrict__ orow = out + (size_t)y * pitch;
+        for (int x = lane; x < w; x += 32) {
+          const double u = (x == w - 1 && w > 1) ? (double)(W - 1) : __dmul_rn((double)x, stepx);
+          const int u0 = min(max((int)floor(u), 0), W - 2);
+          const double ua = __dsub_rn((double)(u0 + 1), u), ub = __dsub_rn(u, (double)u0);
+          const float w1 = (float)__dmul_rn(ua, va), w2 = (float)__dmul_rn(ub, va);
+          const float w3 = (float)__dmul_rn(ua, vb), w4 = (float)__dmul_rn(ub, vb);
+          float r[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* pl = base + c * plane;
-      r[c] = sfm_blend(w1, w2, w3, w4, __ldg(pl + a00), __ldg(pl + a00 + 1), __ldg(pl + a10), __ldg(pl + a10 + 1));
+          for (int c = 0; c < 3; ++c) {
+            const float* pl = r0 + c * plane + u0;
+            r[c] = sfm_blend(w1, w2, w3, w4, __ldg(pl), __ldg(pl + 1), __ldg(pl + W), __ldg(pl + W + 1));
+          }
+          orow[x] = make_float4(r[0], r[1], r[2], 0.f);
+        }
+        if (is_src && lane == 0) orow[w] = zero4;
+      }
     }
-    o.x = r[0];
-    o.y = r[1];
-    o.z = r[2];
+    // the two zero rows below a source image belong to the last band
+    if (is_src && band == n_bands - 1)
+      for (int k = threadIdx.x; k < 2 * pitch; k += kPrepThreads) out[(size_t)h * pitch + k] = zero4;
   }
-  *out = o;
 }
 
 __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float* __restrict__ out, long long n_img,
@@ -160,21 +129,8 @@ __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float*
 
 int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
   SfmPrepParams p = p_in;
-  // vector path for scale 0 needs 16-byte aligned planes and rows
-  p.vec0 = (p.do_pyramid && p.W % 4 == 0 && ((uintptr_t)p.tgt & 15) == 0 && ((uintptr_t)p.src & 15) == 0) ? 1 : 0;
-  long long total = 0;
-  for (int s = 0; s < SFM_MAX_SCALES; ++s) {
-    p.pix_begin[s] = total;
-    if (s < p.ns && p.do_pyramid) {
-      const long long n = (long long)p.B * (1 + p.S) * (p.H >> s) * (p.W >> s);
-      total += (s == 0 && p.vec0) ? n / 4 : n;
-    }
-  }
-  p.n_pyr_blocks = (int)((total + kPrepThreads - 1) / kPrepThreads);
-  long long n_pad = 0;
-  if (p.do_pyramid)
-    for (int s = 0; s < p.ns; ++s) n_pad += (long long)p.B * p.S * ((p.H >> s) + 2ll * sfm_src_pitch(p.W >> s));
-  const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1 + n_pad;
+  p.n_pyr_blocks = p.do_pyramid ? p.B * (1 + p.S) * ((p.H + kBand - 1) / kBand) : 0;
+  const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;
   const int tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
   sfm_prep_kernel<<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
   SFM_CUDA_CHECK(cudaGetLastError());

@@ -40,10 +40,14 @@ __global__ void __launch_bounds__(256) sfm_smooth_kernel(const __grid_constant__
   const int b = t / p.tiles_y[s];
   const int x0 = tx * TS, y0 = ty * TS;
   const float* __restrict__ D = p.disp[s] + (size_t)b * h * w;
-  for (int k = threadIdx.x; k < TP * TP; k += 256) {
-    const int ly = k / TP, lx = k - ly * TP;
-    const int yy = y0 - HALO + ly, xx = x0 - HALO + lx;
-    sd[ly][lx] = ((unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w) ? __ldg(D + (size_t)yy * w + xx) : 0.f;
+  for (int ly = threadIdx.x >> 5; ly < TP; ly += 8) {          // a warp per tile row: no index division
+    const int yy = y0 - HALO + ly;
+    const bool yin = (unsigned)yy < (unsigned)h;
+    const float* __restrict__ row = D + (size_t)(yin ? yy : 0) * w;
+    for (int lx = threadIdx.x & 31; lx < TP; lx += 32) {
+      const int xx = x0 - HALO + lx;
+      sd[ly][lx] = (yin && (unsigned)xx < (unsigned)w) ? __ldg(row + xx) : 0.f;
+    }
   }
   __syncthreads();
   const float k_dx2 = p.sm_dx2[s], k_mix = p.sm_mix[s], k_dy2 = p.sm_dy2[s];
