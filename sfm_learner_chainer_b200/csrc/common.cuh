@@ -224,9 +224,17 @@ __device__ __forceinline__ float sfm_warp_sum(float v) {
 }
 
 // dL/dpose (6) from dL/dT (3x4, fp64) through T = [R|t], R = (Rx.Ry).Rz   
+__device__ __forceinline__ void sfm_pose_backward_cs(const float* pose, const float* cf, const float* sf, const double* dT,
+                                                     float* gpose);
 __device__ __forceinline__ void sfm_pose_backward(const float* pose, const double* dT, float* gpose) {
-  float cf[3], sf[3], Xf[9], Yf[9], Zf[9];
+  float cf[3], sf[3];
   sfm_euler_sincos(pose, cf, sf);
+  sfm_pose_backward_cs(pose, cf, sf, dT, gpose);
+}
+// same with the sin/cos of the clipped angles supplied by the caller
+__device__ __forceinline__ void sfm_pose_backward_cs(const float* pose, const float* cf, const float* sf, const double* dT,
+                                                     float* gpose) {
+  float Xf[9], Yf[9], Zf[9];
   sfm_rot_mats(cf, sf, Xf, Yf, Zf);
   double X[9], Y[9], Z[9], A[9], GR[9], GA[9], GRz[9], GRx[9], GRy[9];
   for (int k = 0; k < 9; ++k) { X[k] = Xf[k]; Y[k] = Yf[k]; Z[k] = Zf[k]; }

@@ -33,8 +33,10 @@ int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, in
 struct SfmFusedParams {
   int B, S, ns;
   int h[SFM_MAX_SCALES], w[SFM_MAX_SCALES];
-  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];   // CTA-tile decomposition (SSIM tile kernel)
+  // strip decomposition of the smoothness kernel: tiles_x = strips, tiles_y = row segments of sm_hseg rows
+  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];
   int tile_begin[SFM_MAX_SCALES + 1];
+  int sm_hseg;
   // warp-task decomposition (marching kernels): a warp owns a 32-column strip x hseg rows of one (snippet, scale)
   int hseg;
   int nstrip[SFM_MAX_SCALES], nseg[SFM_MAX_SCALES];

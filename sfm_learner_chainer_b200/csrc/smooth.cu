@@ -6,17 +6,22 @@
 //
 // The term depends on the disparity alone, so it runs as its own small stencil kernel ahead of the
 // fused photometric kernel: it writes gdisp completely (every pixel, zero where no term touches it) and
-// the fused kernel then accumulates the photometric gradient on top.  A CTA owns a 32x32 tile staged
-// with a 2-pixel halo in shared memory; the gradient is evaluated in gather form (each pixel sums the
-// signs of the second differences it takes part in), so there is no scatter and no atomic on gdisp.
+// the fused kernel then accumulates the photometric gradient on top.
+//
+// Marching formulation (same shape as the SSIM kernel): a warp owns a strip of 28 interior columns (+2
+// halo columns per side) x hseg rows and streams the disparity rows y0-2 .. y1+1 through registers, lane =
+// column.  Horizontal neighbours come from warp shuffles (6 per row), vertical ones from short register
+// rings.  With S2x, S2y, M the signed weights of the second differences (0 where the difference does not
+// exist) the gradient is the gather
+//   G(y,x) = [S2x(y,x-2) - 2 S2x(y,x-1) + S2x(y,x)] + [S2y(y-2,x) - 2 S2y(y-1,x) + S2y(y,x)]
+//          + [M(y,x) - M(y,x-1)] - [M(y-1,x) - M(y-1,x-1)]
+// so there is no scatter and no atomic on gdisp.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace {
 
-constexpr int TS = 32;            // tile edge
-constexpr int HALO = 2;
-constexpr int TP = TS + 2 * HALO; // padded tile edge
+constexpr int SM_IW = 28;         // interior columns per strip
 
 __device__ __forceinline__ float sgnc(float v, float c) {   // sign(v) * c (c > 0), 0 when v == 0
   const float t = __int_as_float((__float_as_int(v) & 0x80000000) | __float_as_int(c));
@@ -24,103 +29,111 @@ __device__ __forceinline__ float sgnc(float v, float c) {   // sign(v) * c (c > 
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(256) sfm_smooth_kernel(const __grid_constant__ SfmFusedParams p) {
-  __shared__ float sd[TP][TP + 1];
-  __shared__ float s_red[8];
-  // ---- tile decode (uniform)
+__global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ SfmFusedParams p) {
+  const int lane = threadIdx.x;
+  // ---- task decode (uniform): strips x row segments of every (snippet, scale)
   int t = blockIdx.x, s = 0;
 #pragma unroll
   for (int q = 1; q < SFM_MAX_SCALES; ++q)
     if (q < p.ns && t >= p.tile_begin[q]) s = q;
   t -= p.tile_begin[s];
   const int h = p.h[s], w = p.w[s];
-  const int tx = t % p.tiles_x[s];
-  t /= p.tiles_x[s];
-  const int ty = t % p.tiles_y[s];
-  const int b = t / p.tiles_y[s];
-  const int x0 = tx * TS, y0 = ty * TS;
+  const int seg = t % p.tiles_y[s];
+  t /= p.tiles_y[s];
+  const int strip = t % p.tiles_x[s];
+  const int b = t / p.tiles_x[s];
+  const int y0 = seg * p.sm_hseg, y1 = min(y0 + p.sm_hseg, h);
+  const int xx = strip * SM_IW - 2 + lane;
+  const bool col_in = (xx >= 0) && (xx < w);
+  const bool col_own = (lane >= 2) && (lane < 2 + SM_IW) && (xx < w);
   const float* __restrict__ D = p.disp[s] + (size_t)b * h * w;
-  for (int ly = threadIdx.x >> 5; ly < TP; ly += 8) {          // a warp per tile row: no index division
-    const int yy = y0 - HALO + ly;
-    const bool yin = (unsigned)yy < (unsigned)h;
-    const float* __restrict__ row = D + (size_t)(yin ? yy : 0) * w;
-    for (int lx = threadIdx.x & 31; lx < TP; lx += 32) {
-      const int xx = x0 - HALO + lx;
-      sd[ly][lx] = (yin && (unsigned)xx < (unsigned)w) ? __ldg(row + xx) : 0.f;
-    }
-  }
-  __syncthreads();
+  float* __restrict__ G = GRAD ? p.gdisp[s] + (size_t)b * h * w : nullptr;
   const float k_dx2 = p.sm_dx2[s], k_mix = p.sm_mix[s], k_dy2 = p.sm_dy2[s];
   const float gyv = (GRAD && p.gy) ? __ldg(p.gy) : 1.f;
-  const int lx = (threadIdx.x & 31) + HALO;
-  const int x = x0 + (threadIdx.x & 31);
+  const bool x_dx2 = col_in && (xx <= w - 3);          // dx2(., xx) exists
+  const bool x_mix = col_in && (xx <= w - 2);          // cell (., xx) exists
   float loss = 0.f;
-#pragma unroll
-  for (int rr = 0; rr < TS / 8; ++rr) {
-    const int ly = (threadIdx.x >> 5) + rr * 8 + HALO;
-    const int y = y0 + ly - HALO;
-    if (x < w && y < h) {
-      const float c = sd[ly][lx];
-      const float xm2 = sd[ly][lx - 2], xm1 = sd[ly][lx - 1], xp1 = sd[ly][lx + 1], xp2 = sd[ly][lx + 2];
-      const float ym2 = sd[ly - 2][lx], ym1 = sd[ly - 1][lx], yp1 = sd[ly + 1][lx], yp2 = sd[ly + 2][lx];
-      const float mm = sd[ly - 1][lx - 1], mp = sd[ly - 1][lx + 1], pm = sd[ly + 1][lx - 1], pp = sd[ly + 1][lx + 1];
-      const float ex_m2 = __fsub_rn(xm1, xm2), ex_m1 = __fsub_rn(c, xm1), ex_0 = __fsub_rn(xp1, c), ex_p1 = __fsub_rn(xp2, xp1);
-      const float ey_m2 = __fsub_rn(ym1, ym2), ey_m1 = __fsub_rn(c, ym1), ey_0 = __fsub_rn(yp1, c), ey_p1 = __fsub_rn(yp2, yp1);
-      const float dx2_m2 = __fsub_rn(ex_m1, ex_m2), dx2_m1 = __fsub_rn(ex_0, ex_m1), dx2_0 = __fsub_rn(ex_p1, ex_0);
-      const float dy2_m2 = __fsub_rn(ey_m1, ey_m2), dy2_m1 = __fsub_rn(ey_0, ey_m1), dy2_0 = __fsub_rn(ey_p1, ey_0);
-      // 2x2 cells touching the centre: dxdy = (D11 - D10) - (D01 - D00) ; dydx = (D11 - D01) - (D10 - D00)
-      const float a00 = __fsub_rn(__fsub_rn(pp, yp1), ex_0), b00 = __fsub_rn(__fsub_rn(pp, xp1), ey_0);      // cell (y, x)
-      const bool x0ok = x <= w - 3, y0ok = y <= h - 3, c00 = (x <= w - 2) && (y <= h - 2);
-      loss += (x0ok ? fabsf(dx2_0) * k_dx2 : 0.f) + (y0ok ? fabsf(dy2_0) * k_dy2 : 0.f) +
-              (c00 ? (fabsf(a00) + fabsf(b00)) * k_mix : 0.f);
-      if (GRAD) {
-        const float a01 = __fsub_rn(__fsub_rn(yp1, pm), ex_m1), b01 = __fsub_rn(ey_0, __fsub_rn(pm, xm1));   // cell (y, x-1)
-        const float a10 = __fsub_rn(ex_0, __fsub_rn(mp, ym1)), b10 = __fsub_rn(__fsub_rn(xp1, mp), ey_m1);   // cell (y-1, x)
-        const float a11 = __fsub_rn(ex_m1, __fsub_rn(ym1, mm)), b11 = __fsub_rn(ey_m1, __fsub_rn(xm1, mm));  // cell (y-1, x-1)
-        float g = 0.f;
-        g += (x >= 2) ? sgnc(dx2_m2, k_dx2) : 0.f;
-        g -= (x >= 1 && x <= w - 2) ? 2.f * sgnc(dx2_m1, k_dx2) : 0.f;
-        g += x0ok ? sgnc(dx2_0, k_dx2) : 0.f;
-        g += (y >= 2) ? sgnc(dy2_m2, k_dy2) : 0.f;
-        g -= (y >= 1 && y <= h - 2) ? 2.f * sgnc(dy2_m1, k_dy2) : 0.f;
-        g += y0ok ? sgnc(dy2_0, k_dy2) : 0.f;
-        g += c00 ? (sgnc(a00, k_mix) + sgnc(b00, k_mix)) : 0.f;                                   // centre = D00
-        g -= (x >= 1 && y <= h - 2) ? (sgnc(a01, k_mix) + sgnc(b01, k_mix)) : 0.f;                // centre = D01
-        g -= (y >= 1 && x <= w - 2) ? (sgnc(a10, k_mix) + sgnc(b10, k_mix)) : 0.f;                // centre = D10
-        g += (x >= 1 && y >= 1) ? (sgnc(a11, k_mix) + sgnc(b11, k_mix)) : 0.f;                    // centre = D11
-        p.gdisp[s][(size_t)b * h * w + (size_t)y * w + x] = gyv * g;
-      }
+  // rings (row index relative to the row r being loaded)
+  float d1 = 0.f;                   // D[r-1]
+  float ex1 = 0.f;                  // ex[r-1]
+  float ey2 = 0.f;                  // ey[r-2] = D[r-1] - D[r-2]
+  float sy3 = 0.f, sy4 = 0.f;       // S2y[r-3], S2y[r-4]
+  float n2 = 0.f, n3 = 0.f;         // N[r-2], N[r-3],  N[y] = M(y,x) - M(y,x-1)
+  float gx1 = 0.f, gx2 = 0.f;       // Gx[r-1], Gx[r-2]
+  auto load = [&](int r) { return (col_in && r >= 0 && r < h) ? __ldg(D + (size_t)r * w + xx) : 0.f; };
+  float d_next = load(y0 - 2);
+#pragma unroll 1
+  for (int r = y0 - 2; r < y1 + 2; ++r) {
+    const float d0 = d_next;
+    d_next = load(r + 1);
+    const bool r_in = (r >= 0) && (r < h);
+    // ---- horizontal terms of row r
+    const float ex0 = __fsub_rn(__shfl_down_sync(0xffffffffu, d0, 1), d0);                 // D[r][x+1] - D[r][x]
+    const float dx2 = __fsub_rn(__shfl_down_sync(0xffffffffu, ex0, 1), ex0);
+    const bool vx = r_in && x_dx2;
+    const float sx = vx ? sgnc(dx2, k_dx2) : 0.f;
+    if (vx && col_own && r >= y0 && r < y1) loss += fabsf(dx2) * k_dx2;
+    const float sxm1 = __shfl_up_sync(0xffffffffu, sx, 1), sxm2 = __shfl_up_sync(0xffffffffu, sx, 2);
+    const float gx0 = (sxm2 - 2.f * sxm1) + sx;
+    // ---- vertical terms: dy2 at row r-2
+    const float ey1 = __fsub_rn(d0, d1);                                                    // D[r] - D[r-1]
+    const float dy2 = __fsub_rn(ey1, ey2);
+    const int ry = r - 2;
+    const bool vy = col_in && (ry >= 0) && (ry <= h - 3);
+    const float sy2 = vy ? sgnc(dy2, k_dy2) : 0.f;
+    if (vy && col_own && ry >= y0 && ry < y1) loss += fabsf(dy2) * k_dy2;
+    // ---- mixed terms of cell (r-1, x): dxdy = ex[r] - ex[r-1] ; dydx = ey[r-1][x+1] - ey[r-1][x]
+    const float a = __fsub_rn(ex0, ex1);
+    const float bq = __fsub_rn(__shfl_down_sync(0xffffffffu, ey1, 1), ey1);
+    const int rm = r - 1;
+    const bool vm = x_mix && (rm >= 0) && (rm <= h - 2);
+    const float m1 = vm ? (sgnc(a, k_mix) + sgnc(bq, k_mix)) : 0.f;
+    if (vm && col_own && rm >= y0 && rm < y1) loss += (fabsf(a) + fabsf(bq)) * k_mix;
+    const float n1 = m1 - __shfl_up_sync(0xffffffffu, m1, 1);
+    // ---- gradient of pixel (r-2, x)
+    if (GRAD) {
+      const float g = (gx2 + ((sy4 - 2.f * sy3) + sy2)) + (n2 - n3);
+      if (col_own && ry >= y0 && ry < y1) G[(size_t)ry * w + xx] = gyv * g;
     }
+    d1 = d0; ex1 = ex0; ey2 = ey1;
+    sy4 = sy3; sy3 = sy2;
+    n3 = n2; n2 = n1;
+    gx2 = gx1; gx1 = gx0;
   }
   loss = sfm_warp_sum(loss);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = loss;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) tot += s_red[k];
-    if (tot != 0.f) atomicAdd(p.acc + 1, (double)tot);
-  }
+  if (lane == 0 && loss != 0.f) atomicAdd(p.acc + 1, (double)loss);
 }
 
 }  // namespace
 
-// Fills tiles_x/tiles_y/tile_begin of `p` and launches.  With grad != 0 every gdisp[s] is fully written.
+// Fills the strip decomposition (tiles_x = strips, tiles_y = row segments, tile_begin) of `p` and launches.
+// With grad != 0 every gdisp[s] is fully written.
 int sfm_launch_smooth(SfmFusedParams& p, int grad, cudaStream_t stream) {
+  // segment height: enough warps to cover the chip a few times, few enough that the 4 extra rows stay cheap
+  long long strips = 0;
+  for (int s = 0; s < p.ns; ++s) strips += (long long)p.B * ((p.w[s] + SM_IW - 1) / SM_IW);
+  int hseg = 64;
+  while (hseg > 8) {
+    long long n = 0;
+    for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SM_IW - 1) / SM_IW) * ((p.h[s] + hseg - 1) / hseg);
+    if (n >= 148 * 4 * 8) break;
+    hseg >>= 1;
+  }
+  p.sm_hseg = hseg;
   int total = 0;
   for (int s = 0; s < SFM_MAX_SCALES; ++s) {
     p.tile_begin[s] = total;
     if (s < p.ns) {
-      p.tiles_x[s] = (p.w[s] + TS - 1) / TS;
-      p.tiles_y[s] = (p.h[s] + TS - 1) / TS;
+      p.tiles_x[s] = (p.w[s] + SM_IW - 1) / SM_IW;
+      p.tiles_y[s] = (p.h[s] + hseg - 1) / hseg;
       total += p.B * p.tiles_x[s] * p.tiles_y[s];
     } else {
       p.tiles_x[s] = p.tiles_y[s] = 1;
     }
   }
   p.tile_begin[SFM_MAX_SCALES] = total;
-  if (grad) sfm_smooth_kernel<true><<<total, 256, 0, stream>>>(p);
-  else sfm_smooth_kernel<false><<<total, 256, 0, stream>>>(p);
+  if (grad) sfm_smooth_kernel<true><<<total, 32, 0, stream>>>(p);
+  else sfm_smooth_kernel<false><<<total, 32, 0, stream>>>(p);
   SFM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

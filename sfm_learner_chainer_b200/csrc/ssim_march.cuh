@@ -54,10 +54,11 @@ template <int N>
 struct IC { static constexpr int value = N; };
 
 #ifndef SFM_MINB_SSIM
-#define SFM_MINB_SSIM 10
+#define SFM_MINB_SSIM 12
 #endif
 template <bool GRAD, bool ACCUM, bool DEBUG>
 __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
+  __shared__ float4 sP[3];
   const int lane = threadIdx.x;
   const StripTask t = decode_strip(p, blockIdx.x);
   const int s = t.s, b = t.b, h = p.h[s], w = p.w[s], S = p.S;
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   const float inv_n3 = p.inv_n3[s];
   const float wpix = gyv * (1.f - p.ssim_rate) * inv_n3;
   const float wssim = gyv * p.ssim_rate * inv_n3;
-  const float c1v = 0.01f * 0.01f, c2v = 0.03f * 0.03f, k9 = 1.f / 9.f;
+  // SSIM on raw 3x3 window SUMS (9 x the means): the 1/81 factors of numerator and denominator cancel
+  const float C1 = 81.f * (0.01f * 0.01f), C2 = 81.f * (0.03f * 0.03f);
   const float* __restrict__ kinvp = p.kinv + ((size_t)b * p.ns + s) * 9;
   const float xf = (float)xx;
   const float kk0 = __ldg(kinvp + 0), kk1 = __ldg(kinvp + 1), kk2 = __ldg(kinvp + 2);
@@ -83,15 +85,13 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   float* __restrict__ gdisp = GRAD ? p.gdisp[s] + (size_t)b * plane : nullptr;
   const size_t src_img = (size_t)sfm_src_rows(h) * geo.pitch;
   float pix_part = 0.f, ssim_part = 0.f;
-  const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end)
+  const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end) are warped
 
   for (int i = 0; i < S; ++i) {
-    float P[12];
-    {
-      const float* __restrict__ pp = p.proj + (((size_t)b * S + i) * p.ns + s) * 12;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = __ldg(pp + k);
-    }
+    __syncwarp();
+    if (lane < 12) reinterpret_cast<float*>(sP)[lane] = __ldg(p.proj + (((size_t)b * S + i) * p.ns + s) * 12 + lane);
+    __syncwarp();
+    const float P3 = sP[0].w, P7 = sP[1].w, P11 = sP[2].w;
     float accA[3] = {0.f, 0.f, 0.f}, accB[3] = {0.f, 0.f, 0.f}, accC[3] = {0.f, 0.f, 0.f};
     const bool first = (i == 0);
     const float4* __restrict__ img = p.src_pyr[s] + ((size_t)b * S + i) * src_img;
@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
     float hs[3][15], gs[3][9];
     Rec rec[3];
     bool mask[3];                                        // all-zero mask of the row's pixel (base_model.py:96)
+    float dq[3];                                         // disparity / target rows fetched ahead
+    float4 Tq[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
 #pragma unroll
       for (int c = 0; c < 3; ++c) rec[k].Ix[c] = rec[k].Iy[c] = rec[k].P[c] = rec[k].T[c] = 0.f;
       rec[k].q0 = rec[k].q1 = rec[k].q2 = rec[k].r = rec[k].depth = 0.f;
+      dq[k] = 1.f;
+      Tq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     auto load_dT = [&](int r, float& dd, float4& TT) {
       dd = 1.f;
@@ -118,39 +122,68 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         TT = __ldg(tgt + r * w + xx);
       }
     };
-    float dA, dB;            // disparity / target of rows r, r+1 (fetched ahead)
-    float4 TA, TB;
-    load_dT(r_begin, dA, TA);
-    load_dT(r_begin + 1, dB, TB);
+    // pending row: projected, gathers in flight, consumed by the next step
+    float4 I00, I01, I10, I11;
+    float pwa = 0.f, pwb = 0.f, pwc = 0.f, pwd = 0.f, pq0 = 0.f, pq1 = 0.f, pq2 = 0.f, pr = 0.f, pdepth = 0.f;
+    float g_old = 0.f;
+
+    // refill: project row r (its disparity was fetched a step earlier), issue its gathers, fetch row r+1's
+    // disparity / target and the partial gdisp of the row whose backward runs in the next step
+    auto refill = [&](auto SLOT, const int r) {
+      constexpr int sl = decltype(SLOT)::value, nx = (sl + 1) % 3;
+      const bool in_img = col_in && (r >= 0) && (r < h) && (r < r_end);
+      const float d = dq[sl];
+      pdepth = rcp_newton(d);
+      const float yf = (float)r;
+      const float rx = __fadd_rn(__fadd_rn(rxx, __fmul_rn(kk1, yf)), kk2);
+      const float ry = __fadd_rn(__fadd_rn(ryx, __fmul_rn(kk4, yf)), kk5);
+      const float rz = __fadd_rn(__fadd_rn(rzx, __fmul_rn(kk7, yf)), kk8);
+      const float X = __fmul_rn(pdepth, rx), Y = __fmul_rn(pdepth, ry), Z = __fmul_rn(pdepth, rz);
+      float P[12];
+      {
+        const float4 a = sP[0], bb = sP[1], c = sP[2];
+        P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
+        P[4] = bb.x; P[5] = bb.y; P[6] = bb.z; P[7] = bb.w;
+        P[8] = c.x; P[9] = c.y; P[10] = c.z; P[11] = c.w;
+      }
+      PairFwd f;
+      pair_project(P, X, Y, Z, geo, f, in_img);
+      pwa = f.wa; pwb = f.wb; pwc = f.wc; pwd = f.wd;
+      pq0 = f.q0; pq1 = f.q1; pq2 = f.q2; pr = f.r;
+      const float4* __restrict__ tp = img + f.idx;
+      I00 = __ldg(tp);
+      I01 = __ldg(tp + 1);
+      I10 = __ldg(tp + geo.pitch);
+      I11 = __ldg(tp + geo.pitch + 1);
+      load_dT(r + 1, dq[nx], Tq[nx]);
+      if (GRAD && (ACCUM || !first)) {
+        const int rf = r - 2;
+        g_old = (col_own && rf >= t.y0 && rf < t.y1) ? gdisp[rf * w + xx] : 0.f;
+      }
+      if (DEBUG && in_img && col_own && (r >= t.y0) && (r < t.y1) && p.dbg_u0[s]) {
+        const size_t o = ((size_t)b * S + i) * plane + (size_t)r * w + xx;
+        SfmCoord c;
+        sfm_project(P, X, Y, Z, w, h, geo.hw, geo.hh, c);
+        p.dbg_u0[s][o] = f.inb ? (int)(f.idx % (unsigned)geo.pitch) : c.u0;
+        p.dbg_v0[s][o] = f.inb ? (int)(f.idx / (unsigned)geo.pitch) : c.v0;
+        p.dbg_inb[s][o] = f.inb ? 1 : 0;
+      }
+    };
 
     auto step = [&](auto PH, const int r) {
       constexpr int cur = decltype(PH)::value, pv1 = (cur + 2) % 3, pv2 = (cur + 1) % 3;
-      // ---------------- early loads: the row two ahead, the partial gdisp of the row whose backward runs now
-      float dC;
-      float4 TC;
-      load_dT(r + 2, dC, TC);
       const int rf = r - 2;
       const bool do_f = col_own && rf >= t.y0 && rf < t.y1;
-      float g_old = 0.f;
-      if (GRAD && (ACCUM || !first) && do_f) g_old = gdisp[rf * w + xx];
-      // ---------------- stage A: warp pixel (r, lane)
-      const bool in_img = col_in && (r >= 0) && (r < h);
+      const float g_prev = g_old;
+      // ---------------- stage A: blend pixel (r, lane) from the taps gathered during the previous step
       Rec& rc_ = rec[cur];
       {
-        const float d = dA;
-        const float4 T = TA;
-        const float depth = rcp_newton(d);
-        const float yf = (float)r;
-        const float rx = __fadd_rn(__fadd_rn(rxx, __fmul_rn(kk1, yf)), kk2);
-        const float ry = __fadd_rn(__fadd_rn(ryx, __fmul_rn(kk4, yf)), kk5);
-        const float rz = __fadd_rn(__fadd_rn(rzx, __fmul_rn(kk7, yf)), kk8);
-        const float X = __fmul_rn(depth, rx), Y = __fmul_rn(depth, ry), Z = __fmul_rn(depth, rz);
-        PairFwd f;
-        pair_project(P, X, Y, Z, geo, f, in_img);
-        const float4* __restrict__ tp = img + f.idx;
-        const float4 I00 = __ldg(tp), I01 = __ldg(tp + 1), I10 = __ldg(tp + geo.pitch), I11 = __ldg(tp + geo.pitch + 1);
-        float P0, P1, P2;
-        pair_blend(f, I00, I01, I10, I11, P0, P1, P2);
+        const float4 T = Tq[cur];
+        const float w1 = __fmul_rn(pwa, pwc), w2 = __fmul_rn(pwb, pwc);
+        const float w3 = __fmul_rn(pwa, pwd), w4 = __fmul_rn(pwb, pwd);
+        const float P0 = sfm_blend(w1, w2, w3, w4, I00.x, I01.x, I10.x, I11.x);
+        const float P1 = sfm_blend(w1, w2, w3, w4, I00.y, I01.y, I10.y, I11.y);
+        const float P2 = sfm_blend(w1, w2, w3, w4, I00.z, I01.z, I10.z, I11.z);
         const bool m = (P0 == 0.f) && (P1 == 0.f) && (P2 == 0.f);               // true outside the image / view
         const bool own = col_own && (r >= t.y0) && (r < t.y1);
         pix_part += (own && !m) ? (fabsf(P0 - T.x) + fabsf(P1 - T.y) + fabsf(P2 - T.z)) : 0.f;
@@ -158,34 +191,36 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         rc_.P[0] = P0; rc_.P[1] = P1; rc_.P[2] = P2;
         rc_.T[0] = T.x; rc_.T[1] = T.y; rc_.T[2] = T.z;
         if (GRAD) {
-          rc_.Ix[0] = f.wc * (I01.x - I00.x) + f.wd * (I11.x - I10.x);
-          rc_.Ix[1] = f.wc * (I01.y - I00.y) + f.wd * (I11.y - I10.y);
-          rc_.Ix[2] = f.wc * (I01.z - I00.z) + f.wd * (I11.z - I10.z);
-          rc_.Iy[0] = f.wa * (I10.x - I00.x) + f.wb * (I11.x - I01.x);
-          rc_.Iy[1] = f.wa * (I10.y - I00.y) + f.wb * (I11.y - I01.y);
-          rc_.Iy[2] = f.wa * (I10.z - I00.z) + f.wb * (I11.z - I01.z);
-          rc_.q0 = f.q0; rc_.q1 = f.q1; rc_.q2 = f.q2; rc_.r = f.r;
-          rc_.depth = depth;
+          rc_.Ix[0] = pwc * (I01.x - I00.x) + pwd * (I11.x - I10.x);
+          rc_.Ix[1] = pwc * (I01.y - I00.y) + pwd * (I11.y - I10.y);
+          rc_.Ix[2] = pwc * (I01.z - I00.z) + pwd * (I11.z - I10.z);
+          rc_.Iy[0] = pwa * (I10.x - I00.x) + pwb * (I11.x - I01.x);
+          rc_.Iy[1] = pwa * (I10.y - I00.y) + pwb * (I11.y - I01.y);
+          rc_.Iy[2] = pwa * (I10.z - I00.z) + pwb * (I11.z - I01.z);
+          rc_.q0 = pq0; rc_.q1 = pq1; rc_.q2 = pq2; rc_.r = pr;
+          rc_.depth = pdepth;
         }
-        if (DEBUG && own) {
-          const size_t im = (size_t)b * S + i;
-          const size_t pix = (size_t)r * w + xx;
-          debug_dump(p, s, im * plane + pix, im * 3 * plane + pix, plane, P, X, Y, Z, w, h, geo, f, P0, P1, P2);
+        keep_live(I00.w); keep_live(I01.w); keep_live(I10.w); keep_live(I11.w); keep_live(T.w);
+        if (DEBUG && own && p.dbg_P[s]) {
+          float* o = p.dbg_P[s] + ((size_t)b * S + i) * 3 * plane + (size_t)r * w + xx;
+          o[0] = P0;
+          o[plane] = P1;
+          o[2 * (size_t)plane] = P2;
         }
       }
-      dA = dB; TA = TB;
-      dB = dC; TB = TC;
+      // ---------------- refill for row r + 1: its gathers fly while stages B..F of this step run
+      refill(IC<pv2>{}, r + 1);          // slot of row r+1 in the 3-ring == (cur + 1) % 3
       // ---------------- stage B: row sums of P, P^2, P.T, T, T^2 over lanes-1..+1 (zero outside the image)
       {
         float* h0 = hs[cur];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float pv = rc_.P[c], tv = rc_.T[c];
-          const float pl = __shfl_up_sync(0xffffffffu, pv, 1), pr = __shfl_down_sync(0xffffffffu, pv, 1);
+          const float pl = __shfl_up_sync(0xffffffffu, pv, 1), prr = __shfl_down_sync(0xffffffffu, pv, 1);
           const float tl = __shfl_up_sync(0xffffffffu, tv, 1), tr = __shfl_down_sync(0xffffffffu, tv, 1);
-          h0[c * 5 + 0] = (pl + pv) + pr;
-          h0[c * 5 + 1] = fmaf(pr, pr, fmaf(pv, pv, pl * pl));
-          h0[c * 5 + 2] = fmaf(pr, tr, fmaf(pv, tv, pl * tl));
+          h0[c * 5 + 0] = (pl + pv) + prr;
+          h0[c * 5 + 1] = fmaf(prr, prr, fmaf(pv, pv, pl * pl));
+          h0[c * 5 + 2] = fmaf(prr, tr, fmaf(pv, tv, pl * tl));
           h0[c * 5 + 3] = (tl + tv) + tr;
           h0[c * 5 + 4] = fmaf(tr, tr, fmaf(tv, tv, tl * tl));
         }
@@ -203,27 +238,33 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         const float lw = (live_px && own_c) ? 1.f : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float a = ((h2[c * 5 + 0] + h1[c * 5 + 0]) + h0[c * 5 + 0]) * k9;
-          const float s2 = ((h2[c * 5 + 1] + h1[c * 5 + 1]) + h0[c * 5 + 1]) * k9;
-          const float cc = ((h2[c * 5 + 2] + h1[c * 5 + 2]) + h0[c * 5 + 2]) * k9;
-          const float my = ((h2[c * 5 + 3] + h1[c * 5 + 3]) + h0[c * 5 + 3]) * k9;
-          const float tt = ((h2[c * 5 + 4] + h1[c * 5 + 4]) + h0[c * 5 + 4]) * k9;
-          const float aa = a * a, mm = my * my, am = a * my;
-          const float sx = s2 - aa, sy = tt - mm, sxy = cc - am;
-          const float n1 = fmaf(2.f, am, c1v), n2 = fmaf(2.f, sxy, c2v);
-          const float d1v = (aa + mm) + c1v, d2v = (sx + sy) + c2v;
+          // window sums: Sp = 9a, Spp = 9 A(P^2), Spt = 9 A(PT), St = 9 my, Stt = 9 A(T^2)
+          const float Sp = (h2[c * 5 + 0] + h1[c * 5 + 0]) + h0[c * 5 + 0];
+          const float Spp = (h2[c * 5 + 1] + h1[c * 5 + 1]) + h0[c * 5 + 1];
+          const float Spt = (h2[c * 5 + 2] + h1[c * 5 + 2]) + h0[c * 5 + 2];
+          const float St = (h2[c * 5 + 3] + h1[c * 5 + 3]) + h0[c * 5 + 3];
+          const float Stt = (h2[c * 5 + 4] + h1[c * 5 + 4]) + h0[c * 5 + 4];
+          // 81 x the reference's quantities: n1 = 2 a my + c1, n2 = 2 sxy + c2, d1 = a^2 + my^2 + c1, d2 = sx + sy + c2
+          const float pp = Sp * Sp, tt = St * St, pt = Sp * St;
+          const float n1 = fmaf(2.f, pt, C1);
+          const float n2 = fmaf(2.f, fmaf(9.f, Spt, -pt), C2);
+          const float d1v = (pp + tt) + C1;
+          const float d2v = (fmaf(9.f, Spp, -pp) + fmaf(9.f, Stt, -tt)) + C2;
           const float n = n1 * n2, dd = d1v * d2v;
           const float rd = rcp_approx(dd);
-          const float q = n * rd;
+          const float q = n * rd;                          // SSIM
           const float raw = fmaf(-0.5f, q, 0.5f);
           ssim_part = fmaf(__saturatef(raw), lw, ssim_part);
           if (GRAD) {
+            // d raw / d(Sp, Spp, Spt) with n, d in the 81x units (SURVEY A.7 rescaled):
+            //   g_n = dL/dn = -0.5 w / d ; g_d = dL/dd = 0.5 w n / d^2
+            //   dn/dSp = 2 St (n2 - n1) ; dn/dSpt = 18 n1 ; dd/dSp = 2 Sp (d2 - d1) ; dd/dSpp = 9 d1
             const bool live = live_px && (raw >= 0.f) && (raw <= 1.f);     // F.clip passes gradient inside [0, 1]
             const float g_n = live ? (-0.5f * wssim) * rd : 0.f;
             const float g_d = -g_n * q;
-            g0[c * 3 + 0] = fmaf(g_n * my, n2 - n1, (g_d * a) * (d2v - d1v));   // g_a / 2
-            g0[c * 3 + 1] = g_d * d1v;                                           // g_s
-            g0[c * 3 + 2] = g_n * n1;                                            // g_c / 2
+            g0[c * 3 + 0] = fmaf(g_n * St, n2 - n1, (g_d * Sp) * (d2v - d1v));   // (dL/dSp) / 2
+            g0[c * 3 + 1] = g_d * d1v;                                            // (dL/dSpp) / 9
+            g0[c * 3 + 2] = g_n * n1;                                             // (dL/dSpt) / 18
           }
         }
       }
@@ -246,31 +287,39 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
           const float Aa = (g2[c * 3 + 0] + g1[c * 3 + 0]) + gh0[c * 3 + 0];
           const float As = (g2[c * 3 + 1] + g1[c * 3 + 1]) + gh0[c * 3 + 1];
           const float Ac = (g2[c * 3 + 2] + g1[c * 3 + 2]) + gh0[c * 3 + 2];
-          // dL/dP = A(g_a) + 2P.A(g_s) + T.A(g_c), A = 3x3 mean; g_a, g_c carry a factor 1/2
-          const float gsv = (2.f * k9) * fmaf(rb.T[c], Ac, fmaf(rb.P[c], As, Aa));
-          gP[c] = gsv + ((mf || !do_f) ? 0.f : sign_times(rb.P[c] - rb.T[c], wpix));
-          gP[c] = do_f ? gP[c] : 0.f;
+          // dL/dP = sum over the 3x3 windows containing the pixel of dL/dSp + 2P dL/dSpp + T dL/dSpt
+          //       = 2 Aa + 18 P As + 18 T Ac
+          const float gsv = fmaf(18.f, fmaf(rb.T[c], Ac, rb.P[c] * As), 2.f * Aa);
+          const float gl1 = mf ? 0.f : sign_times(rb.P[c] - rb.T[c], wpix);
+          gP[c] = do_f ? gsv + gl1 : 0.f;
         }
         // sampler + projection backward; out-of-view pixels have Ix = Iy = 0 and r = 0
         const float gu = gP[0] * rb.Ix[0] + gP[1] * rb.Ix[1] + gP[2] * rb.Ix[2];
         const float gv = gP[0] * rb.Iy[0] + gP[1] * rb.Iy[1] + gP[2] * rb.Iy[2];
         const float gq0 = gu * rb.r, gq1 = gv * rb.r;
         const float gq2 = -(gq0 * rb.q0 + gq1 * rb.q1) * rb.r;
-        const float gdd = gq0 * (rb.q0 - P[3]) + gq1 * (rb.q1 - P[7]) + gq2 * (rb.q2 - P[11]);
+        const float gdd = gq0 * (rb.q0 - P3) + gq1 * (rb.q1 - P7) + gq2 * (rb.q2 - P11);
         const float yfb = (float)rf;
         const float e0 = gq0 * rb.depth, e1 = gq1 * rb.depth, e2 = gq2 * rb.depth;
         accA[0] += e0; accA[1] += e1; accA[2] += e2;
         accB[0] = fmaf(e0, yfb, accB[0]); accB[1] = fmaf(e1, yfb, accB[1]); accB[2] = fmaf(e2, yfb, accB[2]);
         accC[0] += gq0; accC[1] += gq1; accC[2] += gq2;
-        if (do_f) gdisp[rf * w + xx] = g_old - gdd * rb.depth;
+        float* gp = gdisp + rf * w + xx;
+        const float gval = g_prev - gdd * rb.depth;
+        if (do_f) *gp = gval;
       }
     };
 
+    // prologue: rows r_begin (slot 0) and its lookahead
+    load_dT(r_begin, dq[0], Tq[0]);
+    refill(IC<0>{}, r_begin);
+    // the row loop always runs whole groups of three steps (ring rotation = renaming); rows past r_end are
+    // out of range everywhere (loads predicated off, nothing owned)
 #pragma unroll 1
     for (int r = r_begin; r < r_end; r += 3) {
       step(IC<0>{}, r);
-      if (r + 1 < r_end) step(IC<1>{}, r + 1);
-      if (r + 2 < r_end) step(IC<2>{}, r + 2);
+      step(IC<1>{}, r + 1);
+      step(IC<2>{}, r + 2);
     }
     // ---- flush: expand (A, B, C) to dL/dP = sum gq (x) (X, Y, Z, 1) with X = depth*((k0 x + k2) + k1 y) ...
     const bool last = (i == S - 1);
