@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of libsfmloss.so (see include/sfmloss.h for the contract and the
 // reference interfaces each one replaces).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -30,6 +31,15 @@ extern "C" int sfm_set_kernel_events(void* start_event, void* stop_event) {
   return 0;
 }
 extern "C" int sfm_version(void) { return SFM_VERSION; }
+
+bool sfm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SFM_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 int sfm_validate_desc(const SfmDesc* d) {
   if (!d) { sfm_set_error("SfmDesc is NULL"); return SFM_E_NULL_POINTER; }

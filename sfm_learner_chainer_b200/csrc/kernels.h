@@ -73,6 +73,26 @@ struct SfmFusedParams {
   uint8_t* dbg_inb[SFM_MAX_SCALES];
 };
 
+// Launch helper: with pdl != 0 the kernel is a programmatic dependent launch on the previous kernel of the
+// stream (its CTAs may be scheduled while the predecessor drains; the kernel itself orders its dependent
+// accesses with cudaGridDependencySynchronize()).  SFM_NO_PDL=1 in the environment disables it.
+bool sfm_pdl_enabled();
+template <typename K, typename... Args>
+static inline cudaError_t sfm_launch_kernel(K kernel, unsigned grid, unsigned block, cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool use = pdl && sfm_pdl_enabled();
+  cfg.attrs = use ? attr : nullptr;
+  cfg.numAttrs = use ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // mode bits for the launcher
 enum { SFM_MODE_EXP = 1, SFM_MODE_SSIM = 2, SFM_MODE_GRAD = 4, SFM_MODE_DEBUG = 8 };
 int sfm_launch_fused(SfmFusedParams& p, int mode, cudaStream_t stream);

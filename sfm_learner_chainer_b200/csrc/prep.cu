@@ -22,6 +22,7 @@ constexpr int kBand = 8;          // full-resolution rows per pyramid CTA
 // two rows below the image.
 __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_constant__ SfmPrepParams p) {
   const int blk = blockIdx.x;
+  cudaTriggerProgrammaticLaunchCompletion();      // the smoothness kernel may start once every CTA of this grid runs
   if (blk >= p.n_pyr_blocks) {
     // ---- tables + accumulator reset (a handful of trailing CTAs)
     const int t = (blk - p.n_pyr_blocks) * kPrepThreads + threadIdx.x;

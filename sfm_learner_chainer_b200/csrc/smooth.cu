@@ -31,6 +31,7 @@ __device__ __forceinline__ float sgnc(float v, float c) {   // sign(v) * c (c > 
 template <bool GRAD>
 __global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ SfmFusedParams p) {
   const int lane = threadIdx.x;
+  cudaTriggerProgrammaticLaunchCompletion();
   // ---- task decode (uniform): strips x row segments of every (snippet, scale)
   int t = blockIdx.x, s = 0;
 #pragma unroll
@@ -101,6 +102,8 @@ __global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ 
     gx2 = gx1; gx1 = gx0;
   }
   loss = sfm_warp_sum(loss);
+  // everything above depends only on the caller's disparity; the loss cell is reset by the prep kernel
+  cudaGridDependencySynchronize();
   if (lane == 0 && loss != 0.f) atomicAdd(p.acc + 1, (double)loss);
 }
 
@@ -132,8 +135,7 @@ int sfm_launch_smooth(SfmFusedParams& p, int grad, cudaStream_t stream) {
     }
   }
   p.tile_begin[SFM_MAX_SCALES] = total;
-  if (grad) sfm_smooth_kernel<true><<<total, 32, 0, stream>>>(p);
-  else sfm_smooth_kernel<false><<<total, 32, 0, stream>>>(p);
-  SFM_CUDA_CHECK(cudaGetLastError());
+  if (grad) SFM_CUDA_CHECK(sfm_launch_kernel(sfm_smooth_kernel<true>, total, 32, stream, true, p));
+  else SFM_CUDA_CHECK(sfm_launch_kernel(sfm_smooth_kernel<false>, total, 32, stream, true, p));
   return 0;
 }

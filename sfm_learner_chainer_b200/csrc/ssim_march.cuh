@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   const size_t src_img = (size_t)sfm_src_rows(h) * geo.pitch;
   float pix_part = 0.f, ssim_part = 0.f;
   const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end) are warped
+  cudaTriggerProgrammaticLaunchCompletion();           // lets the epilogue's CTAs become resident while this grid drains
+  cudaGridDependencySynchronize();                     // pyramid, tables (prep kernel) and gdisp (smoothness kernel) are complete
 
   for (int i = 0; i < S; ++i) {
     __syncwarp();
@@ -346,8 +348,7 @@ template <typename K>
 static int launch_ssim_kernel(K kernel, const SfmFusedParams& p, cudaStream_t stream) {
   const int n_tasks = p.task_begin[SFM_MAX_SCALES];
   if (sfm_ev_start) SFM_CUDA_CHECK(cudaEventRecord(sfm_ev_start, stream));
-  kernel<<<n_tasks, 32, 0, stream>>>(p);
-  SFM_CUDA_CHECK(cudaGetLastError());
+  SFM_CUDA_CHECK(sfm_launch_kernel(kernel, n_tasks, 32, stream, !sfm_ev_start, p));
   if (sfm_ev_stop) SFM_CUDA_CHECK(cudaEventRecord(sfm_ev_stop, stream));
   return 0;
 }
