@@ -414,6 +414,7 @@ def run_b200(args):
 
     total_pix = wl.pix * world
     value = total_pix / (ms * 1e-3) / 1e6
+    n_launch = 3 + (1 if c['smooth_reg'] else 0)       # prep, [smooth], fused, epilogue
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload='%s: %s' % (args.config, describe(args.config)), per_gpu_batch=wl.B,
@@ -421,21 +422,33 @@ def run_b200(args):
                             parallelism='snippet-sharded x%d, async 5-float loss allreduce' % world if world > 1 else 'single GPU',
                             l2_policy='inputs+outputs rotated over %d buffer sets (%.0f MB > 2 x L2 %.0f MB)' % (
                                 wl.nsets, wl.nsets * wl.A_strict / 1e6, wl.l2_bytes / 1e6),
-                            launch='CUDA graph replay (prep + fused + epilogue kernel nodes)' if not args.no_graph else 'direct C-ABI calls',
+                            launch=('CUDA graph replay of the step\'s %d kernel nodes (pyramid/tables, %sfused loss, epilogue; '
+                                    'programmatic dependent launches between them)' % (n_launch, 'smoothness, ' if c['smooth_reg'] else ''))
+                            if not args.no_graph else 'direct C-ABI calls',
                             units='target-pyramid pixels = B * sum_s h_s*w_s (%d per step per GPU)' % wl.pix),
-                clocks=clocks, gpu_launches=3 * args.steps)
+                clocks=clocks, gpu_launches=n_launch * args.steps)
 
     if rank == 0:
         # ---- roofline of the dominant kernel (fused loss), events around the kernel itself
         k_mean, k_med = wl.time_fused_kernel(200)
         ach = wl.A_kernel / (k_mean * 1e-3) / 1e9
-        line['roofline'] = dict(bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+        traffic, issue = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_latest.json')))[args.config]
+            traffic = prof.get('dram_bytes')             # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            issue = prof
+        except Exception:
+            pass
+        line['roofline'] = dict(bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic,
                                 kernel='sfm_fused_%s_kernel' % ('ssim' if (c['ssim_rate'] and not c['exp_reg']) else 'l1'),
                                 kernel_us=k_mean * 1e3, kernel_us_median=k_med * 1e3,
                                 algorithmic_bytes=wl.A_kernel, peak_source=peak_src,
                                 byte_model='4*B*sum_hw*(3 + 3S + 2 + exp*2S): NHWC4 pyramid in, disp in, gdisp out (+logits/glogits)',
                                 note='at B=4 the roofline time is ~2 us (below launch latency): latency-bound; '
-                                     'see other_configs for the bandwidth-relevant shapes')
+                                     'see other_configs for the bandwidth-relevant shapes.  The fused kernels are '
+                                     'FP32-issue bound, not HBM bound (DESIGN.md section 5): ncu of the same kernel in '
+                                     'profiles/ncu_latest.json',
+                                ncu=issue)
         ach_s = wl.A_strict / (ms * 1e-3) / 1e9
         line['roofline_step'] = dict(bound='hbm', achieved=ach_s, peak=peak, unit='GB/s', frac=ach_s / peak,
                                      algorithmic_bytes=wl.A_strict,
