@@ -82,15 +82,15 @@ def cpu_oracle_run(cfg_name, n_iters, threads):
         return O.sfm_loss(d['tgt'][sl], d['src'][sl], d['intrinsics'][sl], [x[sl] for x in d['disps']],
                           d['poses'][sl], [x[sl] for x in d['logits']], cfg)[0]
 
-    threads = max(1, min(threads, B))
-    times = []
+    # every (step, snippet) pair is an independent unit of host work: all of them go through one thread pool so
+    # that the arm uses every host core it can even when B is smaller than the core count
+    threads = max(1, min(threads, B * max(1, n_iters)))
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(one, range(min(B, threads))))                        # warm-up (page-in, caches)
-        for _ in range(n_iters):
-            t0 = time.perf_counter()
-            list(ex.map(one, range(B)))
-            times.append(time.perf_counter() - t0)
-    return float(np.median(times)), threads, (B, S, H, W)
+        t0 = time.perf_counter()
+        list(ex.map(one, [b for _ in range(n_iters) for b in range(B)]))
+        sec = (time.perf_counter() - t0) / n_iters
+    return float(sec), threads, (B, S, H, W)
 
 
 def run_reference(args):
@@ -102,7 +102,7 @@ def run_reference(args):
     sec, threads, (B, S, H, W) = cpu_oracle_run(args.config, max(1, args.steps), ncpu)
     pix = B * pyramid_pixels(H, W)
     val = pix / sec / 1e6
-    sample = '%d full %s steps (B=%d, S=%d, %dx%d, 4 scales), snippets sharded over %d threads' % (
+    sample = '%d full %s steps (B=%d, S=%d, %dx%d, 4 scales), (step, snippet) units over a pool of %d threads' % (
         max(1, args.steps), args.config, B, S, H, W, threads)
     line = dict(impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=max(1, args.steps),
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -519,6 +519,8 @@ def main():
     if args.impl == 'reference':
         if args.steps > 20:
             args.steps = 20            # bounded sample: each step is ~0.2-0.8 s of host work
+        if args.steps < 8:
+            args.steps = 8             # enough (step, snippet) units to occupy the host cores
         run_reference(args)
     else:
         run_b200(args)
