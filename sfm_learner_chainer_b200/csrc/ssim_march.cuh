@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   const float wssim = gyv * p.ssim_rate * inv_n3;
   // SSIM on raw 3x3 window SUMS (9 x the means): the 1/81 factors of numerator and denominator cancel
   const float C1 = 81.f * (0.01f * 0.01f), C2 = 81.f * (0.03f * 0.03f);
+  cudaTriggerProgrammaticLaunchCompletion();           // lets the epilogue's CTAs become resident while this grid drains
+  // everything below reads what the prep kernel (pyramid, tables) and the smoothness kernel (gdisp) wrote
+  cudaGridDependencySynchronize();
   const float* __restrict__ kinvp = p.kinv + ((size_t)b * p.ns + s) * 9;
   const float xf = (float)xx;
   const float kk0 = __ldg(kinvp + 0), kk1 = __ldg(kinvp + 1), kk2 = __ldg(kinvp + 2);
@@ -86,8 +89,6 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   const size_t src_img = (size_t)sfm_src_rows(h) * geo.pitch;
   float pix_part = 0.f, ssim_part = 0.f;
   const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end) are warped
-  cudaTriggerProgrammaticLaunchCompletion();           // lets the epilogue's CTAs become resident while this grid drains
-  cudaGridDependencySynchronize();                     // pyramid, tables (prep kernel) and gdisp (smoothness kernel) are complete
 
   for (int i = 0; i < S; ++i) {
     __syncwarp();
