@@ -311,3 +311,30 @@ def test_torch_autograd_bridge_and_model_surface():
     assert_grad_close(host(torch.stack([p.grad for p in poses], 1)), 3.0 * G['gpose'], what='gpose via autograd')
     assert_grad_close(host(disps[2].grad), 3.0 * G['gdisp'][2], what='gdisp via autograd')
     assert_grad_close(host(masks[1].grad), 3.0 * G['glogits'][1], what='glogits via autograd')
+
+
+@pytest.mark.parametrize('flagset', ['v1_ssim', 'v1_odom'])
+def test_back_to_back_calls_are_ordered(flagset):
+    """The four kernels of a step are chained with programmatic dependent launches and consecutive calls share
+    one workspace: many un-synchronised calls on alternating inputs must reproduce the isolated results bit for
+    bit (gdisp / glogits are written without atomics) -- guards the grid-dependency waits."""
+    import torch
+    flags = FLAGSETS[flagset]
+    op = _op(flags)
+    sets = [dev_inputs(make_snippets(4, 2, 128, 416, seed=40 + k)) for k in range(2)]
+    ref = []
+    for g in sets:
+        l, gr = op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+        torch.cuda.synchronize()
+        ref.append((host(l), [host(x) for x in gr['gdisps']], host(gr['gposes'])))
+    outs = []
+    for it in range(24):
+        g = sets[it & 1]
+        outs.append(op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits']))
+    torch.cuda.synchronize()
+    for it, (l, gr) in enumerate(outs):
+        rl, rg, rp = ref[it & 1]
+        np.testing.assert_allclose(host(l), rl, rtol=1e-6)
+        for s in range(4):
+            np.testing.assert_array_equal(host(gr['gdisps'][s]), rg[s])
+        np.testing.assert_allclose(host(gr['gposes']), rp, rtol=1e-5, atol=1e-9)
