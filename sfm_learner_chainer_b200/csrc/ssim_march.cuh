@@ -53,13 +53,24 @@ struct Rec {
 template <int N>
 struct IC { static constexpr int value = N; };
 
+#ifndef SFM_SSIM_FENCE
+#define SFM_SSIM_FENCE 1      // basic-block fence after the refill (see step)
+#endif
+#ifndef SFM_SSIM_SREC
+#define SFM_SSIM_SREC 1       // forward records in shared memory instead of registers
+#endif
 #ifndef SFM_MINB_SSIM
 #define SFM_MINB_SSIM 12
 #endif
 template <bool GRAD, bool ACCUM, bool DEBUG>
 __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
   __shared__ float4 sP[3];
+  // two-row delay line of forward records: [slot][field][lane], written in stage A of row r and read back by
+  // the same lane in stages E/F two steps later (no synchronisation needed).  In registers these 51 values
+  // pushed the kernel over its 168-register budget (17-27 local-memory spills per three rows).
+  __shared__ float sRec[(GRAD && SFM_SSIM_SREC) ? 3 * 17 * 32 : 1];
   const int lane = threadIdx.x;
+  float* const myrec = sRec + lane;
   const StripTask t = decode_strip(p, blockIdx.x);
   const int s = t.s, b = t.b, h = p.h[s], w = p.w[s], S = p.S;
   const Geo geo = make_geo(p, s);
@@ -89,6 +100,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   const size_t src_img = (size_t)sfm_src_rows(h) * geo.pitch;
   float pix_part = 0.f, ssim_part = 0.f;
   const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end) are warped
+  const bool opaque_true = p.hseg != 0x7fffffff;       // always true, unknown to ptxas: basic-block fence (see step)
 
   for (int i = 0; i < S; ++i) {
     __syncwarp();
@@ -114,6 +126,10 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
 #pragma unroll
       for (int c = 0; c < 3; ++c) rec[k].Ix[c] = rec[k].Iy[c] = rec[k].P[c] = rec[k].T[c] = 0.f;
       rec[k].q0 = rec[k].q1 = rec[k].q2 = rec[k].r = rec[k].depth = 0.f;
+      if (GRAD && SFM_SSIM_SREC) {
+#pragma unroll
+        for (int q = 0; q < 17; ++q) myrec[(k * 17 + q) * 32] = 0.f;
+      }
       dq[k] = 1.f;
       Tq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -202,8 +218,23 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
           rc_.Iy[2] = pwa * (I10.z - I00.z) + pwb * (I11.z - I01.z);
           rc_.q0 = pq0; rc_.q1 = pq1; rc_.q2 = pq2; rc_.r = pr;
           rc_.depth = pdepth;
+          if (SFM_SSIM_SREC) {
+            float* o = myrec + cur * 17 * 32;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              o[(0 + c) * 32] = rc_.Ix[c];
+              o[(3 + c) * 32] = rc_.Iy[c];
+              o[(6 + c) * 32] = rc_.P[c];
+              o[(9 + c) * 32] = rc_.T[c];
+            }
+            o[12 * 32] = pq0; o[13 * 32] = pq1; o[14 * 32] = pq2; o[15 * 32] = pr; o[16 * 32] = pdepth;
+          }
         }
+#if SFM_USE_PAD
+        pix_part += pad_sum(I00, I01, I10, I11, T);
+#else
         keep_live(I00.w); keep_live(I01.w); keep_live(I10.w); keep_live(I11.w); keep_live(T.w);
+#endif
         if (DEBUG && own && p.dbg_P[s]) {
           float* o = p.dbg_P[s] + ((size_t)b * S + i) * 3 * plane + (size_t)r * w + xx;
           o[0] = P0;
@@ -213,6 +244,13 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
       }
       // ---------------- refill for row r + 1: its gathers fly while stages B..F of this step run
       refill(IC<pv2>{}, r + 1);          // slot of row r+1 in the 3-ring == (cur + 1) % 3
+      // Basic-block fence.  The refill has no consumer before the next step, so ptxas' critical-path scheduler
+      // otherwise sinks the projection and the four gathers to the end of the step (seen in the SASS; ncu:
+      // half of all stall samples were long-scoreboard waits on the taps ~60 instructions after their issue).
+      // A branch it cannot fold keeps them ahead of stages B..F, which then cover the latency.
+#if SFM_SSIM_FENCE
+      if (opaque_true) {
+#endif
       // ---------------- stage B: row sums of P, P^2, P.T, T, T^2 over lanes-1..+1 (zero outside the image)
       {
         float* h0 = hs[cur];
@@ -282,7 +320,22 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         // ---------------- stages E + F: dL/dP and the warp backward for pixel (rf = r-2, lane)
         const float* g1 = gs[pv1];
         const float* g2 = gs[pv2];
+#if SFM_SSIM_SREC
+        Rec rb;
+        {
+          const float* o = myrec + pv2 * 17 * 32;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            rb.Ix[c] = o[(0 + c) * 32];
+            rb.Iy[c] = o[(3 + c) * 32];
+            rb.P[c] = o[(6 + c) * 32];
+            rb.T[c] = o[(9 + c) * 32];
+          }
+          rb.q0 = o[12 * 32]; rb.q1 = o[13 * 32]; rb.q2 = o[14 * 32]; rb.r = o[15 * 32]; rb.depth = o[16 * 32];
+        }
+#else
         const Rec& rb = rec[pv2];
+#endif
         const bool mf = mask[pv2];
         float gP[3];
 #pragma unroll
@@ -311,6 +364,9 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         const float gval = g_prev - gdd * rb.depth;
         if (do_f) *gp = gval;
       }
+#if SFM_SSIM_FENCE
+      }
+#endif
     };
 
     // prologue: rows r_begin (slot 0) and its lookahead
