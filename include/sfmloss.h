@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SFM_VERSION 100           /* major*100 + minor */
+#define SFM_VERSION 101           /* major*100 + minor */
 #define SFM_MAX_SCALES 4          /* base_model.py:66 (len(pred_depthes) == 4) */
 #define SFM_MAX_SOURCES 8         /* seq_len-1; shipped configs use 2 and 4 */
 
@@ -62,14 +62,27 @@ typedef struct SfmDesc {
   float exp_reg;
   float ssim_rate;
   uint32_t flags;
+  /* Producer-side fusion at the seam with the two CNNs (both default to 0 = off):
+   * raw_disp_scales  bit s set: disps[s] holds the PRE-activation output of DispNet's `dispout` convolution
+   *                  and the kernels apply disp = DISP_SCALING * sigmoid(x) + MIN_DISP themselves
+   *                  (models/disp_net.py:7-8,104,110,116,122); gdisps[s] is then the gradient w.r.t. x.
+   *                  Scale 0 (disp1) is consumed by the loss alone; disp2..4 are also fed back into the
+   *                  decoder (disp_net.py:105,111,117), so a drop-in normally sets bit 0 only.
+   * raw_pose_hw      n > 0: poses holds PoseNet's `poseout` map (B, 6*S, n) with n = h'*w' spatial positions
+   *                  and the kernels apply pose = 0.01 * mean over n (models/pose_net.py:51-53); gposes then
+   *                  has the same (B, 6*S, n) shape.  n <= 128.                                             */
+  uint32_t raw_disp_scales;
+  int32_t raw_pose_hw;
 } SfmDesc;
 
 /* Inputs of one loss evaluation.  Shapes as produced by the reference's nets and dataset:
  *   tgt        (B,3,H,W)            base_model.py:48
  *   src        (B,S,3,H,W)          base_model.py:57-58 (== stacked (B,3S,H,W))
  *   intrinsics (B,n_scales,3,3)     datasets/kitti/kitti_raw_transformed.py:76-93
- *   disps[s]   (B,1,H>>s,W>>s)      models/disp_net.py:124   (disparity, NOT depth)
- *   poses      (B,S,6)              models/pose_net.py:52-54 (rx,ry,rz,tx,ty,tz per source)
+ *   disps[s]   (B,1,H>>s,W>>s)      models/disp_net.py:124   (disparity, NOT depth; pre-activation map when
+ *                                   bit s of desc->raw_disp_scales is set)
+ *   poses      (B,S,6)              models/pose_net.py:52-54 (rx,ry,rz,tx,ty,tz per source); (B,6*S,n) raw
+ *                                   `poseout` map when desc->raw_pose_hw = n > 0
  *   logits[s]  (B,S,H>>s,W>>s)      models/pose_net.py:56-67; may be NULL when exp_reg <= 0
  *   proj       (B,S,n_scales,3,4)   only with SFM_FLAG_TABLES_PROVIDED: K4.T rows 0..2 (transform.py:86-88)
  *   kinv       (B,n_scales,3,3)     only with SFM_FLAG_TABLES_PROVIDED: inverse intrinsics (transform.py:105)
@@ -152,6 +165,14 @@ int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, int scale, fl
  * including the five blocking host<->device copies per (scale, source) of models/utils.py:33-84. */
 int sfm_build_tables(const SfmDesc* desc, const float* poses, const float* intrinsics, float* proj_out,
                      float* kinv_out, void* stream);
+
+/* Stage API of the producer-side fusions (the same device code the fused kernels inline; the parity tests
+ * use it to show raw-input mode == activation stage + plain mode bit for bit):
+ * sfm_disp_activation: disp[k] = DISP_SCALING * sigmoid(x[k]) + MIN_DISP (disp_net.py:104) for n elements,
+ * optional dact[k] = d disp / d x.   sfm_pose_reduce: x (B, 6*S, hw) -> poses (B, S, 6) = 0.01 * mean
+ * (pose_net.py:52-53). */
+int sfm_disp_activation(long long n, const float* x, float* disp, float* dact, void* stream);
+int sfm_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, void* stream);
 
 /* Stage API: projective_inverse_warp(imgs, depthes, poses, K) of transform.py:156-165 on N images of
  * one resolution.  imgs (N,3,h,w) NCHW, depth (N,h*w) [the reference passes it broadcast to 3 rows],

@@ -23,6 +23,8 @@ function by function after the reference (citations are relative to
 * ``models/base_model.py:126-142`` compute_ssim
 * ``models/base_model.py:157-167`` compute_exp_reg_loss
 * ``models/base_model.py:169-185`` compute_smooth_loss
+* ``models/disp_net.py:7-8,104``  disparity activation  (seam)
+* ``models/pose_net.py:52-53``    pose scaling / spatial mean (seam)
 
 The arithmetic of the reference lives in a third-party dependency that is NOT
 under ``/root/reference`` and NOT installable here: ``chainer==4.0.0b1`` /
@@ -698,6 +700,60 @@ def sfm_loss(tgt, src, intrinsics, disps, poses, logits, cfg,
 
 
 LOSS_KEYS = ('total_loss', 'pixel_loss', 'smooth_loss', 'exp_loss', 'ssim_loss')
+
+
+# --------------------------------------------------------------------------------------------------
+# The seam either side of the loss: the last op of each producer
+# --------------------------------------------------------------------------------------------------
+DISP_SCALING = 10      # models/disp_net.py:7
+MIN_DISP = 0.01        # models/disp_net.py:8
+
+
+def disp_activation(x):
+    """disp = DISP_SCALING * F.sigmoid(x) + MIN_DISP (models/disp_net.py:104,110,116,122) and d disp / d x.
+
+    Chainer's sigmoid is tanh(x * 0.5) * 0.5 + 0.5 (functions/activation/sigmoid.py, forward_cpu) with
+    backward gy * y * (1 - y); the scaling and the offset are separate elementwise ops, each rounded."""
+    t = x.dtype.type
+    y = np.tanh(x * t(0.5)) * t(0.5) + t(0.5)
+    return t(DISP_SCALING) * y + t(MIN_DISP), t(DISP_SCALING) * y * (t(1) - y)
+
+
+def pose_from_raw(x, n_sources):
+    """PoseNet.pred_pose's tail (models/pose_net.py:52-53): 0.01 * F.mean(poseout, (2, 3)) split into
+    n_sources 6-DoF vectors.  x (B, 6*S, h', w') -> (B, S, 6).  numpy reduces the contiguous (h', w') block of
+    a channel with its pairwise fp32 sum."""
+    t = x.dtype.type
+    B = x.shape[0]
+    m = np.ascontiguousarray(x).reshape(B, 6 * n_sources, -1).mean(axis=2, dtype=x.dtype)
+    return (t(0.01) * m).reshape(B, n_sources, 6)
+
+
+def sfm_loss_raw(tgt, src, intrinsics, disps_in, poses_in, logits, cfg, raw_disp_scales=0, raw_pose=False, **kw):
+    """sfm_loss with the seam included: scales in the bit mask `raw_disp_scales` take the pre-activation
+    `dispout` map, `raw_pose` takes the `poseout` map (B, 6*S, h', w').  Gradients are returned w.r.t. what was
+    passed in (chain rule through disp_activation / pose_from_raw)."""
+    S = src.shape[1]
+    disps, dacts = [], []
+    for s, d in enumerate(disps_in):
+        if (raw_disp_scales >> s) & 1:
+            dd, da = disp_activation(d)
+            disps.append(dd)
+            dacts.append(da)
+        else:
+            disps.append(d)
+            dacts.append(None)
+    poses = pose_from_raw(poses_in, S) if raw_pose else poses_in
+    losses, grads, debug = sfm_loss(tgt, src, intrinsics, disps, poses, logits, cfg, **kw)
+    if grads is not None:
+        grads = dict(grads)
+        grads['gdisp'] = [g if da is None else (g.astype(np.float64) * da).astype(g.dtype)
+                          for g, da in zip(grads['gdisp'], dacts)]
+        if raw_pose:
+            n = int(np.prod(poses_in.shape[2:]))
+            gp = grads['gpose'].astype(np.float64).reshape(poses_in.shape[0], 6 * S, *([1] * (poses_in.ndim - 2)))
+            grads['gpose'] = np.broadcast_to(gp * (0.01 / n), poses_in.shape).astype(poses_in.dtype)
+    return losses, grads, dict(debug, disps=disps, poses=poses)
 
 
 def losses_vec(losses):

@@ -62,6 +62,18 @@ int sfm_validate_desc(const SfmDesc* d) {
     sfm_set_error("invalid shape: B*(1+S)*H*W exceeds 2^31 pixels");
     return SFM_E_INVALID_SHAPE;
   }
+  if (d->raw_disp_scales >> d->n_scales) {
+    sfm_set_error("invalid SfmDesc: raw_disp_scales=0x%x names a scale >= n_scales=%d", d->raw_disp_scales, d->n_scales);
+    return SFM_E_INVALID_DESC;
+  }
+  if (d->raw_pose_hw < 0 || d->raw_pose_hw > 128) {
+    sfm_set_error("unsupported SfmDesc: raw_pose_hw=%d (0 = 6-DoF vectors, 1..128 = positions of the poseout map)", d->raw_pose_hw);
+    return SFM_E_UNSUPPORTED;
+  }
+  if (d->raw_pose_hw > 0 && (d->flags & SFM_FLAG_TABLES_PROVIDED)) {
+    sfm_set_error("unsupported SfmDesc: raw_pose_hw > 0 together with SFM_FLAG_TABLES_PROVIDED (the tables are built from the reduced poses)");
+    return SFM_E_UNSUPPORTED;
+  }
   if (!(d->smooth_reg == d->smooth_reg) || !(d->exp_reg == d->exp_reg) || !(d->ssim_rate == d->ssim_rate)) {
     sfm_set_error("invalid SfmDesc: NaN loss weight");
     return SFM_E_INVALID_DESC;
@@ -140,6 +152,8 @@ int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyr
   p.acc = (double*)(ws + L.off_acc);
   p.n_acc = (int)L.acc_doubles;
   p.counter = (unsigned*)(ws + L.off_counter);
+  p.raw_pose_hw = d->raw_pose_hw;
+  p.posevec_out = (float*)(ws + L.off_posevec);
   return sfm_launch_prep(p, st);
 }
 
@@ -191,7 +205,9 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   p.proj = tables ? in->proj : (const float*)(ws + L.off_proj);
   p.kinv = tables ? in->kinv : (const float*)(ws + L.off_kinv);
   p.intrinsics = in->intrinsics;
-  p.poses = in->poses;
+  p.poses = d->raw_pose_hw > 0 ? (const float*)(ws + L.off_posevec) : in->poses;
+  p.raw_pose_hw = d->raw_pose_hw;
+  p.raw_disp_mask = d->raw_disp_scales;
   p.gy = gy;
   p.acc = (double*)(ws + L.off_acc);
   p.counter = (unsigned*)(ws + L.off_counter);
@@ -244,7 +260,7 @@ extern "C" int sfm_scale_grads(const SfmDesc* desc, const float* gy, const SfmGr
     ptrs[n] = grads->gdisps[s]; counts[n++] = desc->B * hw;
     if (m.use_exp) { ptrs[n] = grads->glogits[s]; counts[n++] = (long long)desc->B * desc->S * hw; }
   }
-  ptrs[n] = grads->gposes; counts[n++] = (long long)desc->B * desc->S * 6;
+  ptrs[n] = grads->gposes; counts[n++] = (long long)desc->B * desc->S * 6 * (desc->raw_pose_hw > 0 ? desc->raw_pose_hw : 1);
   return sfm_launch_scale(ptrs, counts, n, gy, (cudaStream_t)stream);
 }
 
@@ -295,7 +311,21 @@ extern "C" int sfm_build_tables(const SfmDesc* desc, const float* poses, const f
   p.intrinsics = intrinsics; p.poses = poses;
   p.proj_out = proj_out; p.kinv_out = kinv_out;
   p.acc = nullptr; p.n_acc = 0; p.counter = nullptr;
+  p.raw_pose_hw = desc->raw_pose_hw; p.posevec_out = nullptr;
   return sfm_launch_prep(p, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_disp_activation(long long n, const float* x, float* disp, float* dact, void* stream) {
+  if (n < 0) { sfm_set_error("sfm_disp_activation: n < 0"); return SFM_E_INVALID_SHAPE; }
+  if (!x || (!disp && !dact)) { sfm_set_error("sfm_disp_activation: null pointer"); return SFM_E_NULL_POINTER; }
+  return sfm_launch_disp_activation(n, x, disp, dact, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, void* stream) {
+  if (B < 1 || S < 1 || S > SFM_MAX_SOURCES) { sfm_set_error("sfm_pose_reduce: invalid B=%d S=%d", B, S); return SFM_E_INVALID_DESC; }
+  if (hw < 1 || hw > 128) { sfm_set_error("sfm_pose_reduce: unsupported hw=%d (1..128)", hw); return SFM_E_UNSUPPORTED; }
+  if (!x || !poses_out) { sfm_set_error("sfm_pose_reduce: null pointer"); return SFM_E_NULL_POINTER; }
+  return sfm_launch_pose_reduce(B, S, hw, x, poses_out, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,8 +384,9 @@ extern "C" int sfm_host_ctx_create(const SfmDesc* desc, SfmHostCtx** ctx_out) {
   HA(c->d_tgt, d->B * img);
   HA(c->d_src, (size_t)d->B * d->S * img);
   HA(c->d_K, (size_t)d->B * d->n_scales * 9 * sizeof(float));
-  HA(c->d_poses, (size_t)d->B * d->S * 6 * sizeof(float));
-  HA(c->d_gposes, (size_t)d->B * d->S * 6 * sizeof(float));
+  const size_t pose_bytes = (size_t)d->B * d->S * 6 * (d->raw_pose_hw > 0 ? d->raw_pose_hw : 1) * sizeof(float);
+  HA(c->d_poses, pose_bytes);
+  HA(c->d_gposes, pose_bytes);
   HA(c->d_losses, 8 * sizeof(float));
   for (int s = 0; s < d->n_scales; ++s) {
     const size_t hw = (size_t)(d->H >> s) * (d->W >> s) * sizeof(float);
@@ -383,7 +414,8 @@ extern "C" int sfm_loss_step_host(SfmHostCtx* c, const SfmInputs* in, float* los
   SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_tgt, in->tgt, d->B * img, cudaMemcpyHostToDevice, st));
   SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_src, in->src, (size_t)d->B * d->S * img, cudaMemcpyHostToDevice, st));
   SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_K, in->intrinsics, (size_t)d->B * d->n_scales * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
-  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_poses, in->poses, (size_t)d->B * d->S * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+  const size_t pose_bytes = (size_t)d->B * d->S * 6 * (d->raw_pose_hw > 0 ? d->raw_pose_hw : 1) * sizeof(float);
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_poses, in->poses, pose_bytes, cudaMemcpyHostToDevice, st));
   SfmInputs din{};
   SfmGrads dg{};
   din.tgt = c->d_tgt; din.src = c->d_src; din.intrinsics = c->d_K; din.poses = c->d_poses;
@@ -402,7 +434,7 @@ extern "C" int sfm_loss_step_host(SfmHostCtx* c, const SfmInputs* in, float* los
   rc = sfm_loss_forward_backward(d, &din, c->d_losses, &dg, c->workspace, st);
   if (rc) return rc;
   SFM_CUDA_CHECK(cudaMemcpyAsync(losses_out, c->d_losses, 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  SFM_CUDA_CHECK(cudaMemcpyAsync(grads->gposes, c->d_gposes, (size_t)d->B * d->S * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SFM_CUDA_CHECK(cudaMemcpyAsync(grads->gposes, c->d_gposes, pose_bytes, cudaMemcpyDeviceToHost, st));
   for (int s = 0; s < d->n_scales; ++s) {
     const size_t hw = (size_t)(d->H >> s) * (d->W >> s) * sizeof(float);
     SFM_CUDA_CHECK(cudaMemcpyAsync(grads->gdisps[s], c->d_gdisp[s], d->B * hw, cudaMemcpyDeviceToHost, st));

@@ -37,6 +37,7 @@ struct SfmWsLayout {
   size_t off_kinv;                 // float  [B][ns][9]
   size_t off_acc;                  // double [4 + B*S*ns*12] loss sums (pixel, smooth, exp, ssim) + dL/dP per scale
   size_t off_counter;              // unsigned: spare
+  size_t off_posevec;              // float  [B][S][6]   6-DoF vectors reduced from the raw `poseout` map (raw_pose_hw > 0)
   size_t acc_doubles;
   size_t total;
 };
@@ -77,6 +78,8 @@ static inline void sfm_ws_layout(const SfmDesc* d, SfmWsLayout* L) {
   off += L->acc_doubles * sizeof(double);
   L->off_counter = off;
   off = sfm_align_up(off + 8, 256);
+  L->off_posevec = off;
+  off = sfm_align_up(off + (size_t)d->B * d->S * 6 * sizeof(float), 256);
   L->total = off;
 }
 
@@ -159,6 +162,40 @@ __device__ __forceinline__ void sfm_ray(const float* kinv, float xf, float yf, f
   rx = __fadd_rn(__fadd_rn(__fmul_rn(kinv[0], xf), __fmul_rn(kinv[1], yf)), kinv[2]);
   ry = __fadd_rn(__fadd_rn(__fmul_rn(kinv[3], xf), __fmul_rn(kinv[4], yf)), kinv[5]);
   rz = __fadd_rn(__fadd_rn(__fmul_rn(kinv[6], xf), __fmul_rn(kinv[7], yf)), kinv[8]);
+}
+
+// ---- producer-side fusions (SfmDesc.raw_disp_scales / raw_pose_hw)
+// disp = DISP_SCALING * F.sigmoid(x) + MIN_DISP (disp_net.py:7-8,104).  Chainer's sigmoid is
+// tanh(x * 0.5) * 0.5 + 0.5 (CPU: numpy.tanh, GPU: the same expression in an elementwise CUDA kernel, i.e.
+// this tanhf); the scaling and the offset are separate elementwise ops, each rounded.  dact = d disp / d x
+// = 10 y (1 - y)  (Sigmoid.backward: gy * y * (1 - y)).
+__device__ __forceinline__ float sfm_disp_act(float x, float& dact) {
+  const float y = __fadd_rn(__fmul_rn(tanhf(__fmul_rn(x, 0.5f)), 0.5f), 0.5f);
+  dact = 10.f * y * (1.f - y);
+  return __fadd_rn(__fmul_rn(10.f, y), 0.01f);
+}
+// fp32 sum of n <= 128 values in numpy's pairwise order (numpy/core/src/umath/loops_utils.h.src, pairwise_sum:
+// sequential for n < 8, otherwise eight running partial sums combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and
+// the tail added sequentially) -- the order F.mean(h, (2, 3)) uses on the contiguous (h', w') block of one
+// channel (pose_net.py:52).
+__device__ __forceinline__ float sfm_np_sum(const float* __restrict__ a, int n) {
+  if (n < 8) {
+    float r = 0.f;                    // numpy seeds the reduction with the first element; 0 + a0 == a0 (also -0: sign irrelevant here)
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  float r[8];
+  for (int k = 0; k < 8; ++k) r[k] = a[k];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], a[i + k]);
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+  return res;
+}
+// pose component = 0.01 * mean(x[0..n))   (pose_net.py:52: float32(0.01) * (sum / n))
+__device__ __forceinline__ float sfm_pose_component(const float* __restrict__ x, int n) {
+  return __fmul_rn(0.01f, __fdiv_rn(sfm_np_sum(x, n), (float)n));
 }
 
 // Everything the sampler needs about one (target pixel, source) pair.

@@ -20,6 +20,8 @@ struct SfmPrepParams {
   double* acc;
   int n_acc;
   unsigned* counter;
+  int raw_pose_hw;   // > 0: `poses` is the raw poseout map (B, 6S, raw_pose_hw); the reduced vectors go to posevec_out
+  float* posevec_out;
   // filled by the launcher
   long long pix_begin[SFM_MAX_SCALES];
   int n_pyr_blocks;
@@ -27,6 +29,8 @@ struct SfmPrepParams {
 };
 
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
+int sfm_launch_disp_activation(long long n, const float* x, float* disp, float* dact, cudaStream_t stream);
+int sfm_launch_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, cudaStream_t stream);
 int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int h, int w, int padded, cudaStream_t stream);
 
 // Fused loss kernel parameters (one launch covers every scale, source and snippet).
@@ -52,7 +56,9 @@ struct SfmFusedParams {
   const float* proj;        // [B][S][ns][12]
   const float* kinv;        // [B][ns][9]
   const float* intrinsics;  // [B][ns][9]
-  const float* poses;       // [B][S][6]
+  const float* poses;       // [B][S][6] (the reduced vectors in the workspace when raw_pose_hw > 0)
+  int raw_pose_hw;          // > 0: gposes has the raw map's shape (B, 6S, raw_pose_hw)
+  unsigned raw_disp_mask;   // bit s: disp[s] is pre-activation, gdisp[s] the gradient w.r.t. it
   const float* gy;          // upstream gradient (device scalar) or nullptr
   double* acc;              // [4 + B*S*12]
   unsigned* counter;

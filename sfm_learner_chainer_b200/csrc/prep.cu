@@ -34,7 +34,15 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
       const int b = t / (p.ns * p.S);
       float K[9], pose[6], P[12];
       for (int k = 0; k < 9; ++k) K[k] = p.intrinsics[((size_t)b * p.ns + s) * 9 + k];
-      for (int k = 0; k < 6; ++k) pose[k] = p.poses[((size_t)b * p.S + i) * 6 + k];
+      if (p.raw_pose_hw > 0) {
+        // producer-side fusion: pose = 0.01 * mean_{h', w'}(poseout)   (pose_net.py:52-53; channel 6i+k of snippet b)
+        for (int k = 0; k < 6; ++k)
+          pose[k] = sfm_pose_component(p.poses + (((size_t)b * p.S + i) * 6 + k) * p.raw_pose_hw, p.raw_pose_hw);
+        if (s == 0 && p.posevec_out)
+          for (int k = 0; k < 6; ++k) p.posevec_out[((size_t)b * p.S + i) * 6 + k] = pose[k];
+      } else {
+        for (int k = 0; k < 6; ++k) pose[k] = p.poses[((size_t)b * p.S + i) * 6 + k];
+      }
       sfm_build_proj(pose, K, P);
       for (int k = 0; k < 12; ++k) p.proj_out[(size_t)t * 12 + k] = P[k];
     } else if (t < n_proj + n_kinv) {
@@ -111,6 +119,22 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
   }
 }
 
+__global__ void sfm_disp_activation_kernel(const float* __restrict__ x, float* __restrict__ disp, float* __restrict__ dact,
+                                           long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float da;
+    const float d = sfm_disp_act(__ldg(x + i), da);
+    if (disp) disp[i] = d;
+    if (dact) dact[i] = da;
+  }
+}
+
+__global__ void sfm_pose_reduce_kernel(const float* __restrict__ x, float* __restrict__ out, int n_comp, int hw) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_comp) out[t] = sfm_pose_component(x + (size_t)t * hw, hw);
+}
+
 __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float* __restrict__ out, long long n_img,
                                           int h, int w, int pitch, int rows) {
   const int hw = h * w;
@@ -134,6 +158,21 @@ int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
   const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;
   const int tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
   sfm_prep_kernel<<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
+  SFM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int sfm_launch_disp_activation(long long n, const float* x, float* disp, float* dact, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const long long blocks = (n + 255) / 256;
+  sfm_disp_activation_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, stream>>>(x, disp, dact, n);
+  SFM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int sfm_launch_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, cudaStream_t stream) {
+  const int n = B * S * 6;
+  sfm_pose_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(x, poses_out, n, hw);
   SFM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

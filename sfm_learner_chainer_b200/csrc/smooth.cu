@@ -61,12 +61,21 @@ __global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ 
   float sy3 = 0.f, sy4 = 0.f;       // S2y[r-3], S2y[r-4]
   float n2 = 0.f, n3 = 0.f;         // N[r-2], N[r-3],  N[y] = M(y,x) - M(y,x-1)
   float gx1 = 0.f, gx2 = 0.f;       // Gx[r-1], Gx[r-2]
-  auto load = [&](int r) { return (col_in && r >= 0 && r < h) ? __ldg(D + (size_t)r * w + xx) : 0.f; };
-  float d_next = load(y0 - 2);
+  // producer-side fusion (SfmDesc.raw_disp_scales): D holds the pre-activation map, the disparity is formed on
+  // load and the gradient is written w.r.t. the raw map (factor ring f0..f2 = d disp / d x of rows r..r-2)
+  const bool raw = (p.raw_disp_mask >> s) & 1u;
+  float f_next = 1.f, f1 = 1.f, f2 = 1.f;
+  auto load = [&](int r, float& f) {
+    f = 1.f;
+    if (!(col_in && r >= 0 && r < h)) return 0.f;
+    const float v = __ldg(D + (size_t)r * w + xx);
+    return raw ? sfm_disp_act(v, f) : v;
+  };
+  float d_next = load(y0 - 2, f_next);
 #pragma unroll 1
   for (int r = y0 - 2; r < y1 + 2; ++r) {
-    const float d0 = d_next;
-    d_next = load(r + 1);
+    const float d0 = d_next, f0 = f_next;
+    d_next = load(r + 1, f_next);
     const bool r_in = (r >= 0) && (r < h);
     // ---- horizontal terms of row r
     const float ex0 = __fsub_rn(__shfl_down_sync(0xffffffffu, d0, 1), d0);                 // D[r][x+1] - D[r][x]
@@ -94,8 +103,9 @@ __global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ 
     // ---- gradient of pixel (r-2, x)
     if (GRAD) {
       const float g = (gx2 + ((sy4 - 2.f * sy3) + sy2)) + (n2 - n3);
-      if (col_own && ry >= y0 && ry < y1) G[(size_t)ry * w + xx] = gyv * g;
+      if (col_own && ry >= y0 && ry < y1) G[(size_t)ry * w + xx] = raw ? (gyv * g) * f2 : gyv * g;
     }
+    f2 = f1; f1 = f0;
     d1 = d0; ex1 = ex0; ey2 = ey1;
     sy4 = sy3; sy3 = sy2;
     n3 = n2; n2 = n1;

@@ -48,6 +48,7 @@ struct Rec {
   float P[3], T[3];
   float q0, q1, q2, r;    // projection, 1/z (0 when out of view)
   float depth;
+  float dsc;              // depth, or depth * (d disp / d x) when the disparity input is the pre-activation map
 };
 
 template <int N>
@@ -62,13 +63,13 @@ struct IC { static constexpr int value = N; };
 #ifndef SFM_MINB_SSIM
 #define SFM_MINB_SSIM 12
 #endif
-template <bool GRAD, bool ACCUM, bool DEBUG>
+template <bool GRAD, bool ACCUM, bool DEBUG, bool RAW>
 __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
   __shared__ float4 sP[3];
   // two-row delay line of forward records: [slot][field][lane], written in stage A of row r and read back by
   // the same lane in stages E/F two steps later (no synchronisation needed).  In registers these 51 values
   // pushed the kernel over its 168-register budget (17-27 local-memory spills per three rows).
-  __shared__ float sRec[(GRAD && SFM_SSIM_SREC) ? 3 * 17 * 32 : 1];
+  __shared__ float sRec[(GRAD && SFM_SSIM_SREC) ? 3 * 18 * 32 : 1];
   const int lane = threadIdx.x;
   float* const myrec = sRec + lane;
   const StripTask t = decode_strip(p, blockIdx.x);
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   cudaGridDependencySynchronize();
   const float* __restrict__ kinvp = p.kinv + ((size_t)b * p.ns + s) * 9;
   const float xf = (float)xx;
+  const bool raw = RAW && ((p.raw_disp_mask >> s) & 1u);    // RAW: some scale takes the pre-activation disparity map
   const float kk0 = __ldg(kinvp + 0), kk1 = __ldg(kinvp + 1), kk2 = __ldg(kinvp + 2);
   const float kk3 = __ldg(kinvp + 3), kk4 = __ldg(kinvp + 4), kk5 = __ldg(kinvp + 5);
   const float kk6 = __ldg(kinvp + 6), kk7 = __ldg(kinvp + 7), kk8 = __ldg(kinvp + 8);
@@ -125,10 +127,10 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
       mask[k] = true;
 #pragma unroll
       for (int c = 0; c < 3; ++c) rec[k].Ix[c] = rec[k].Iy[c] = rec[k].P[c] = rec[k].T[c] = 0.f;
-      rec[k].q0 = rec[k].q1 = rec[k].q2 = rec[k].r = rec[k].depth = 0.f;
+      rec[k].q0 = rec[k].q1 = rec[k].q2 = rec[k].r = rec[k].depth = rec[k].dsc = 0.f;
       if (GRAD && SFM_SSIM_SREC) {
 #pragma unroll
-        for (int q = 0; q < 17; ++q) myrec[(k * 17 + q) * 32] = 0.f;
+        for (int q = 0; q < 18; ++q) myrec[(k * 18 + q) * 32] = 0.f;
       }
       dq[k] = 1.f;
       Tq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
     };
     // pending row: projected, gathers in flight, consumed by the next step
     float4 I00, I01, I10, I11;
-    float pwa = 0.f, pwb = 0.f, pwc = 0.f, pwd = 0.f, pq0 = 0.f, pq1 = 0.f, pq2 = 0.f, pr = 0.f, pdepth = 0.f;
+    float pwa = 0.f, pwb = 0.f, pwc = 0.f, pwd = 0.f, pq0 = 0.f, pq1 = 0.f, pq2 = 0.f, pr = 0.f, pdepth = 0.f, pdsc = 0.f;
     float g_old = 0.f;
 
     // refill: project row r (its disparity was fetched a step earlier), issue its gathers, fetch row r+1's
@@ -151,8 +153,10 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
     auto refill = [&](auto SLOT, const int r) {
       constexpr int sl = decltype(SLOT)::value, nx = (sl + 1) % 3;
       const bool in_img = col_in && (r >= 0) && (r < h) && (r < r_end);
-      const float d = dq[sl];
+      float d = dq[sl], dact = 1.f;
+      if (raw) d = sfm_disp_act(d, dact);      // producer-side fusion: pre-activation disparity map (warp-uniform branch)
       pdepth = rcp_newton(d);
+      if (RAW) pdsc = raw ? pdepth * dact : pdepth;
       const float yf = (float)r;
       const float rx = __fadd_rn(__fadd_rn(rxx, __fmul_rn(kk1, yf)), kk2);
       const float ry = __fadd_rn(__fadd_rn(ryx, __fmul_rn(kk4, yf)), kk5);
@@ -218,8 +222,9 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
           rc_.Iy[2] = pwa * (I10.z - I00.z) + pwb * (I11.z - I01.z);
           rc_.q0 = pq0; rc_.q1 = pq1; rc_.q2 = pq2; rc_.r = pr;
           rc_.depth = pdepth;
+          rc_.dsc = RAW ? pdsc : pdepth;
           if (SFM_SSIM_SREC) {
-            float* o = myrec + cur * 17 * 32;
+            float* o = myrec + cur * 18 * 32;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               o[(0 + c) * 32] = rc_.Ix[c];
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
               o[(9 + c) * 32] = rc_.T[c];
             }
             o[12 * 32] = pq0; o[13 * 32] = pq1; o[14 * 32] = pq2; o[15 * 32] = pr; o[16 * 32] = pdepth;
+            if (RAW) o[17 * 32] = pdsc;
           }
         }
 #if SFM_USE_PAD
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
 #if SFM_SSIM_SREC
         Rec rb;
         {
-          const float* o = myrec + pv2 * 17 * 32;
+          const float* o = myrec + pv2 * 18 * 32;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             rb.Ix[c] = o[(0 + c) * 32];
@@ -332,6 +338,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
             rb.T[c] = o[(9 + c) * 32];
           }
           rb.q0 = o[12 * 32]; rb.q1 = o[13 * 32]; rb.q2 = o[14 * 32]; rb.r = o[15 * 32]; rb.depth = o[16 * 32];
+          rb.dsc = RAW ? o[17 * 32] : rb.depth;
         }
 #else
         const Rec& rb = rec[pv2];
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         accB[0] = fmaf(e0, yfb, accB[0]); accB[1] = fmaf(e1, yfb, accB[1]); accB[2] = fmaf(e2, yfb, accB[2]);
         accC[0] += gq0; accC[1] += gq1; accC[2] += gq2;
         float* gp = gdisp + rf * w + xx;
-        const float gval = g_prev - gdd * rb.depth;
+        const float gval = g_prev - gdd * rb.dsc;
         if (do_f) *gp = gval;
       }
 #if SFM_SSIM_FENCE
@@ -438,15 +445,18 @@ static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug,
   }
   p.task_begin[SFM_MAX_SCALES] = total;
   int rc;
+  const bool raw = p.raw_disp_mask != 0;
+#define SFM_SSIM(GR, AC)                                                                                   \
+  rc = raw ? (debug ? launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, true, true>, p, stream)             \
+                    : launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, false, true>, p, stream))           \
+           : (debug ? launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, true, false>, p, stream)            \
+                    : launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, false, false>, p, stream))
   if (grad) {
-    if (accum) rc = debug ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, true>, p, stream)
-                          : launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false>, p, stream);
-    else rc = debug ? launch_ssim_kernel(sfm_ssim_march_kernel<true, false, true>, p, stream)
-                    : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false>, p, stream);
+    if (accum) { SFM_SSIM(true, true); } else { SFM_SSIM(true, false); }
   } else {
-    rc = debug ? launch_ssim_kernel(sfm_ssim_march_kernel<false, false, true>, p, stream)
-               : launch_ssim_kernel(sfm_ssim_march_kernel<false, false, false>, p, stream);
+    SFM_SSIM(false, false);
   }
+#undef SFM_SSIM
   if (rc) return rc;
   return launch_epilogue(p, stream);
 }

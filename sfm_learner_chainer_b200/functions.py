@@ -19,9 +19,16 @@ class ViewSynthesisLoss(object):
     smooth_reg, exp_reg, ssim_rate: the reference's `architecture:` flags (base_model.py:37-39).
     B_global: batch size every F.mean divides by when the batch is sharded by snippet across
     processes (default: the local batch).
+    raw_disp_scales: bit mask of scales whose `pred_disps[s]` is the PRE-activation `dispout` map; the
+    kernels then apply disp = 10 * sigmoid(x) + 0.01 (models/disp_net.py:104) and return the gradient
+    w.r.t. that map.  raw_pose: `poses` is PoseNet's `poseout` map (B, 6*S, h', w') and the kernels apply
+    0.01 * mean over (h', w') (models/pose_net.py:52-53); `gposes` then has the map's shape.
     """
 
-    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, n_scales=N_SCALES, B_global=None):
+    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, n_scales=N_SCALES, B_global=None,
+                 raw_disp_scales=0, raw_pose=False):
+        self.raw_disp_scales = int(raw_disp_scales)
+        self.raw_pose = bool(raw_pose)
         self.smooth_reg = float(smooth_reg or 0.0)
         self.exp_reg = float(exp_reg or 0.0)
         self.ssim_rate = float(ssim_rate or 0.0)
@@ -35,9 +42,9 @@ class ViewSynthesisLoss(object):
     def use_exp(self):
         return self.exp_reg != 0.0
 
-    def _desc(self, B, S, H, W, flags=0):
+    def _desc(self, B, S, H, W, flags=0, raw_pose_hw=0):
         return L.SfmDesc(B, S, H, W, self.n_scales, int(self.B_global or 0), self.smooth_reg, self.exp_reg,
-                         self.ssim_rate, flags)
+                         self.ssim_rate, flags, self.raw_disp_scales, raw_pose_hw)
 
     def _workspace(self, desc, like):
         key = (desc.B, desc.S, desc.H, desc.W, desc.n_scales, str(getattr(like, 'device', '')))
@@ -59,7 +66,18 @@ class ViewSynthesisLoss(object):
         D.check_array(tgt, 'tgt_img', (B, 3, H, W))
         D.check_array(src, 'src_imgs', (B, S, 3, H, W))
         D.check_array(intrinsics, 'intrinsics', (B, ns, 3, 3))
-        D.check_array(poses, 'poses', (B, S, 6))
+        raw_pose_hw = 0
+        if self.raw_pose:
+            if len(poses.shape) not in (3, 4) or poses.shape[0] != B or poses.shape[1] != 6 * S:
+                raise ValueError('raw poses must be the poseout map (B, 6*S, h\', w\') (pose_net.py:51)')
+            D.check_array(poses, 'poses')
+            raw_pose_hw = 1
+            for n in poses.shape[2:]:
+                raw_pose_hw *= int(n)
+            self._pose_shape = tuple(poses.shape)
+        else:
+            D.check_array(poses, 'poses', (B, S, 6))
+            self._pose_shape = (B, S, 6)
         if len(disps) != ns:
             raise ValueError('expected %d disparity maps, got %d' % (ns, len(disps)))
         flags = 0
@@ -79,13 +97,13 @@ class ViewSynthesisLoss(object):
             D.check_array(kinv, 'kinv', (B, ns, 3, 3))
             inp.proj, inp.kinv = _vp(proj), _vp(kinv)
             flags |= L.SFM_FLAG_TABLES_PROVIDED
-        return self._desc(B, S, H, W, flags), inp
+        return self._desc(B, S, H, W, flags, raw_pose_hw), inp
 
     def _alloc_grads(self, desc, tgt):
         B, S, H, W = desc.B, desc.S, desc.H, desc.W
         g = L.SfmGrads()
         gd = [D.empty(tgt, (B, 1, H >> s, W >> s)) for s in range(self.n_scales)]
-        gp = D.empty(tgt, (B, S, 6))
+        gp = D.empty(tgt, self._pose_shape)
         gl = [D.empty(tgt, (B, S, H >> s, W >> s)) for s in range(self.n_scales)] if self.use_exp else None
         for s in range(self.n_scales):
             g.gdisps[s] = D.ptr(gd[s])
@@ -137,7 +155,8 @@ class ViewSynthesisLoss(object):
 
     def scale_grads(self, grads, gy, B, S, H, W):
         """grads *= gy (device scalar); a no-op on the device when gy == 1."""
-        desc = self._desc(B, S, H, W)
+        gp_shape = tuple(grads['gposes'].shape)
+        desc = self._desc(B, S, H, W, 0, int(gp_shape[2] * (gp_shape[3] if len(gp_shape) > 3 else 1)) if self.raw_pose else 0)
         g = L.SfmGrads()
         for s in range(self.n_scales):
             g.gdisps[s] = D.ptr(grads['gdisps'][s])
@@ -175,6 +194,34 @@ class ViewSynthesisLoss(object):
         L.check(self._lib.sfm_build_tables(C.byref(desc), _vp(poses), _vp(intrinsics), _vp(proj), _vp(kinv),
                                            C.c_void_p(D.current_stream(poses))))
         return proj, kinv
+
+
+def disp_activation(x, want_dact=False):
+    """DISP_SCALING * F.sigmoid(x) + MIN_DISP (models/disp_net.py:7-8,104) as a stage, with the device code
+    the fused kernels inline under `raw_disp_scales`.  -> disp [, d disp / d x]."""
+    D.check_array(x, 'x')
+    n = 1
+    for k in x.shape:
+        n *= int(k)
+    disp = D.empty(x, tuple(x.shape))
+    dact = D.empty(x, tuple(x.shape)) if want_dact else None
+    L.check(L.load().sfm_disp_activation(n, _vp(x), _vp(disp), _vp(dact), C.c_void_p(D.current_stream(x))))
+    return (disp, dact) if want_dact else disp
+
+
+def pose_reduce(x, n_sources):
+    """0.01 * F.mean(poseout, (2, 3)) split into n_sources 6-DoF vectors (models/pose_net.py:52-54):
+    x (B, 6*S, h', w') -> (B, S, 6)."""
+    D.check_array(x, 'x')
+    B = int(x.shape[0])
+    if x.shape[1] != 6 * n_sources:
+        raise ValueError('x.shape[1] must be 6 * n_sources')
+    hw = 1
+    for k in x.shape[2:]:
+        hw *= int(k)
+    out = D.empty(x, (B, n_sources, 6))
+    L.check(L.load().sfm_pose_reduce(B, n_sources, hw, _vp(x), _vp(out), C.c_void_p(D.current_stream(x))))
+    return out
 
 
 def projective_inverse_warp(imgs, depthes, poses, K, proj=None, kinv=None, return_indices=False):

@@ -27,7 +27,7 @@ class SfmDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('S', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('n_scales', C.c_int32), ('B_global', C.c_int32),
                 ('smooth_reg', C.c_float), ('exp_reg', C.c_float), ('ssim_rate', C.c_float),
-                ('flags', C.c_uint32)]
+                ('flags', C.c_uint32), ('raw_disp_scales', C.c_uint32), ('raw_pose_hw', C.c_int32)]
 
 
 class SfmInputs(C.Structure):
@@ -59,6 +59,8 @@ SYMBOLS = {
     'sfm_pyramid': (_i, [_D, _vp, _vp, _vp, _vp]),
     'sfm_pyramid_export': (_i, [_D, _vp, _i, _vp, _vp, _vp]),
     'sfm_build_tables': (_i, [_D, _vp, _vp, _vp, _vp, _vp]),
+    'sfm_disp_activation': (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
+    'sfm_pose_reduce': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'sfm_warp_forward': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'sfm_warp_backward_scratch_bytes': (C.c_size_t, [_i]),
     'sfm_warp_backward': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -84,6 +84,25 @@ def make_snippets(B, S, H, W, seed=0, n_scales=N_SCALES, harsh=False,
                 disps=disps, poses=poses, logits=logits)
 
 
+def make_raw_seam(data, pose_hw=(1, 4), seed=0):
+    """Pre-activation inputs of the seam either side of the loss for the snippets `data` of make_snippets:
+    raw disparity maps x with 10*sigmoid(x)+0.01 ~ data['disps'] (models/disp_net.py:104) and a raw `poseout`
+    map (B, 6*S, h', w') whose 0.01*mean over (h', w') ~ data['poses'] (models/pose_net.py:52)."""
+    rs = np.random.RandomState(seed + 1000)
+    dtype = data['tgt'].dtype
+    raw_disps = []
+    for d in data['disps']:
+        y = np.clip((d.astype(np.float64) - 0.01) / 10.0, 1e-6, 1 - 1e-6)
+        raw_disps.append(np.ascontiguousarray(np.log(y / (1 - y)), dtype=dtype))
+    B, S = data['poses'].shape[:2]
+    ph, pw = pose_hw
+    centre = data['poses'].astype(np.float64).reshape(B, 6 * S, 1, 1) / 0.01
+    noise = rs.standard_normal((B, 6 * S, ph, pw))
+    noise -= noise.mean(axis=(2, 3), keepdims=True)
+    raw_pose = np.ascontiguousarray(centre + 0.5 * np.abs(centre).mean() * noise, dtype=dtype)
+    return raw_disps, raw_pose
+
+
 # BASELINE.json configs -> concrete shapes and reference flag sets (experiments/*.yml)
 CONFIGS = {
     'cfg1': dict(B=4, S=2, H=128, W=416, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0),    # sfm_learner_v1.yml:14-16

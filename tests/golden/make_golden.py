@@ -77,6 +77,80 @@ def run_model(data, flags, dtype):
     return out
 
 
+def run_model_raw(data, raw_disps, raw_pose, flags, dtype):
+    """Same as run_model with the seam on either side of the loss included: the disparities are formed from
+    pre-activation maps with DispNet's expression (models/disp_net.py:104, the reference's own DISP_SCALING /
+    MIN_DISP constants) and the poses by running the reference's own PoseNet.pred_pose (pose_net.py:47-54)
+    on a stand-in `self` whose three convolutions are the identity."""
+    import models.disp_net as ref_disp_net
+    import models.pose_net as ref_pose_net
+    F = chainer.functions
+    reset_reference_caches()
+    chainer.clear_reports()
+    model = ref_base_model.SFMLearner(flags, {'download': None, 'path': None})
+    cast = lambda a: np.ascontiguousarray(a.astype(dtype))
+    xs = [Variable(cast(d)) for d in raw_disps]
+    xp = Variable(cast(raw_pose))
+    S = data['src'].shape[1]
+    masks = [Variable(cast(l)) for l in data['logits']]
+
+    class FakePoseNet(object):
+        n_sources = S
+        activation = staticmethod(lambda h: h)
+        pose1 = pose2 = poseout = staticmethod(lambda h: h)
+
+    def disp_net(tgt):
+        return [ref_disp_net.DISP_SCALING * F.sigmoid(x) + ref_disp_net.MIN_DISP for x in xs]
+
+    def pose_net(tgt, src, do_exp=True):
+        poses = ref_pose_net.PoseNet.pred_pose(FakePoseNet(), xp)
+        return tuple(poses), masks if do_exp else None
+
+    model.disp_net, model.pose_net = disp_net, pose_net
+    K = cast(data['intrinsics'])
+    loss = model(cast(data['tgt']), cast(data['src']), K, K)
+    loss.backward()
+    rep = chainer.get_reports()
+    out = {}
+    for k in ('total_loss', 'pixel_loss', 'smooth_loss', 'exp_loss', 'ssim_loss'):
+        v = rep[k]
+        out[k] = float(v.data) if isinstance(v, Variable) else float(v)
+    out['gx'] = [x.grad for x in xs]
+    out['gxpose'] = xp.grad
+    do_exp = flags['exp_reg'] is not None and flags['exp_reg'] > 0
+    out['glogits'] = [m.grad for m in masks] if do_exp else None
+    return out
+
+
+SEAM_CASES = [
+    ('seam_ssim', 2, 2, 32, 104, 5, (1, 4), dict(smooth_reg=0.1, exp_reg=0, seq_len=3, ssim_rate=0.15)),
+    ('seam_odom', 1, 4, 32, 104, 6, (2, 5), dict(smooth_reg=0.1, exp_reg=0.2, seq_len=5)),
+]
+
+
+def make_seam():
+    from sfm_learner_chainer_b200.synthetic import make_raw_seam
+    for name, B, S, H, W, seed, pose_hw, flags in SEAM_CASES:
+        data = make_snippets(B, S, H, W, seed=seed)
+        raw_disps, raw_pose = make_raw_seam(data, pose_hw, seed=seed)
+        blob = dict(tgt=data['tgt'], src=data['src'], intrinsics=data['intrinsics'], raw_pose=raw_pose,
+                    flags=np.array([flags['smooth_reg'], flags['exp_reg'] or 0.0, flags.get('ssim_rate', 0.0)]))
+        for s in range(4):
+            blob['raw_disp%d' % s] = raw_disps[s]
+            blob['logits%d' % s] = data['logits'][s]
+        for tag, dtype in (('f64', np.float64), ('f32', np.float32)):
+            out = run_model_raw(data, raw_disps, raw_pose, flags, dtype)
+            blob['losses_' + tag] = np.array([out[k] for k in ('total_loss', 'pixel_loss', 'smooth_loss',
+                                                               'exp_loss', 'ssim_loss')], np.float64)
+            blob['gxpose_' + tag] = out['gxpose']
+            for s in range(4):
+                blob['gx%d_%s' % (s, tag)] = out['gx'][s]
+                if out['glogits'] is not None:
+                    blob['glogits%d_%s' % (s, tag)] = out['glogits'][s]
+            print(name, tag, blob['losses_' + tag])
+        np.savez_compressed(os.path.join(HERE, '%s.npz' % name), **blob)
+
+
 def run_warp(data, dtype, scale=0, i=0):
     """projective_inverse_warp (transform.py:156) + its stages at one scale."""
     reset_reference_caches()
@@ -112,6 +186,9 @@ def run_interp(seed):
 
 
 def main():
+    if '--seam-only' in sys.argv:
+        make_seam()
+        return
     for name, B, S, H, W, seed, harsh, flags in CASES:
         data = make_snippets(B, S, H, W, seed=seed, harsh=harsh, rough_disp=(seed % 2 == 1))
         blob = dict(tgt=data['tgt'], src=data['src'], intrinsics=data['intrinsics'], poses=data['poses'],
@@ -137,6 +214,7 @@ def main():
             blob['warp_s%d_img_f64' % sc] = wout['img']
         np.savez_compressed(os.path.join(HERE, 'loss_%s.npz' % name), **blob)
     np.savez_compressed(os.path.join(HERE, 'interp_sampler.npz'), **run_interp(7))
+    make_seam()
     print('golden fixtures written to', HERE)
 
 

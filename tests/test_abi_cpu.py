@@ -26,11 +26,11 @@ def test_every_declared_symbol_is_exported(lib):
     so = lib.load()
     for name in declared:
         assert getattr(so, name) is not None
-    assert so.sfm_version() == 100
+    assert so.sfm_version() == 101
 
 
 def test_struct_layout_matches_header(lib):
-    assert C.sizeof(lib.SfmDesc) == 40
+    assert C.sizeof(lib.SfmDesc) == 48      # 10 x 4 bytes + raw_disp_scales + raw_pose_hw
     assert C.sizeof(lib.SfmInputs) == 8 * (3 + 4 + 1 + 4 + 2)
     assert C.sizeof(lib.SfmGrads) == 8 * 9
     assert C.sizeof(lib.SfmDebug) == 8 * 16
@@ -47,7 +47,9 @@ def test_workspace_and_validation(lib):
                       (lib.SfmDesc(4, 9, 128, 416, 4, 0, 0, 0, 0, 0), 'S=9'),
                       (lib.SfmDesc(4, 2, 16, 416, 4, 0, 0, 0, 0, 0), '2x52'),
                       (lib.SfmDesc(4, 2, 128, 416, 5, 0, 0, 0, 0, 0), 'n_scales=5'),
-                      (lib.SfmDesc(4, 2, 128, 416, 4, 2, 0, 0, 0, 0), 'B_global=2')]:
+                      (lib.SfmDesc(4, 2, 128, 416, 4, 2, 0, 0, 0, 0), 'B_global=2'),
+                      (lib.SfmDesc(4, 2, 128, 416, 4, 0, 0, 0, 0, 0, 0x10, 0), 'raw_disp_scales'),
+                      (lib.SfmDesc(4, 2, 128, 416, 4, 0, 0, 0, 0, 0, 0, 129), 'raw_pose_hw')]:
         assert so.sfm_workspace_bytes(C.byref(bad)) == 0
         assert code in so.sfm_last_error().decode()
     # argument errors come back as negative codes with a message, before any device work
