@@ -20,7 +20,7 @@ class SFMLearner(object):
     """
 
     def __init__(self, config, pretrained_model=None, disp_net=None, pose_net=None, reporter=None,
-                 B_global=None):
+                 B_global=None, raw_disp_scales=0, raw_pose=False):
         self.n_sources = config['seq_len'] - 1
         self.smooth_reg = config['smooth_reg']
         self.exp_reg = config['exp_reg']
@@ -30,7 +30,10 @@ class SFMLearner(object):
         self.reporter = reporter
         self.last_report = {}
         self.last_grads = None
-        self.loss_op = ViewSynthesisLoss(self.smooth_reg, self.exp_reg, self.ssim_rate, B_global=B_global)
+        # raw_disp_scales / raw_pose: the nets stop one op early and the kernels apply the disparity activation
+        # (disp_net.py:104) / the 0.01 * spatial mean (pose_net.py:52) themselves (ViewSynthesisLoss docstring)
+        self.loss_op = ViewSynthesisLoss(self.smooth_reg, self.exp_reg, self.ssim_rate, B_global=B_global,
+                                         raw_disp_scales=raw_disp_scales, raw_pose=raw_pose)
 
     def __call__(self, tgt_img, src_imgs, intrinsics, inv_intrinsics=None):
         batchsize, n_sources, _, H, W = src_imgs.shape
