@@ -312,9 +312,11 @@ class Workload(object):
         return float(np.mean(ts)), float(ts[len(ts) // 2])
 
 
-def run_e2e(cfg_name, steps, device):
+def run_e2e(cfg_name, steps, device, n_ctx=2):
     """Same metric through the host-buffer C-ABI entry point: pinned host inputs -> H2D -> pyramid + fused
-    fwd+bwd -> D2H of the 5 losses and every gradient, each step."""
+    fwd+bwd -> D2H of the five losses and every gradient, EVERY step.  `n_ctx` host contexts are used alternately
+    (sfm_loss_step_host_submit / _wait), the way a data loader keeps the next step's copies in flight while the
+    current one computes; n_ctx=1 is the fully synchronous call.  Returns (Mpix/s, h2d bytes, d2h bytes, loss)."""
     import torch
     from sfm_learner_chainer_b200 import lib as L
     lib = L.load()
@@ -323,37 +325,56 @@ def run_e2e(cfg_name, steps, device):
     exp = c['exp_reg'] != 0
     d = make_snippets(B, S, H, W, seed=1)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    hp = dict(tgt=pin(d['tgt']), src=pin(d['src']), K=pin(d['intrinsics']), poses=pin(d['poses']),
-              disps=[pin(x) for x in d['disps']], logits=[pin(x) for x in d['logits']],
-              gdisps=[pin(np.empty_like(x)) for x in d['disps']], glogits=[pin(np.empty_like(x)) for x in d['logits']],
-              gposes=pin(np.empty_like(d['poses'])), losses=pin(np.zeros(8, np.float32)))
+    hin = dict(tgt=pin(d['tgt']), src=pin(d['src']), K=pin(d['intrinsics']), poses=pin(d['poses']),
+               disps=[pin(x) for x in d['disps']], logits=[pin(x) for x in d['logits']])
     desc = L.SfmDesc(B, S, H, W, 4, 0, c['smooth_reg'], c['exp_reg'], c['ssim_rate'], 0)
-    ctx = C.c_void_p()
-    L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
-    inp, g = L.SfmInputs(), L.SfmGrads()
-    inp.tgt, inp.src, inp.intrinsics, inp.poses = hp['tgt'].data_ptr(), hp['src'].data_ptr(), hp['K'].data_ptr(), hp['poses'].data_ptr()
-    g.gposes = hp['gposes'].data_ptr()
-    h2d = hp['tgt'].numel() * 4 + hp['src'].numel() * 4 + hp['K'].numel() * 4 + hp['poses'].numel() * 4
-    d2h = 5 * 4 + hp['gposes'].numel() * 4
+    inp = L.SfmInputs()
+    inp.tgt, inp.src, inp.intrinsics, inp.poses = hin['tgt'].data_ptr(), hin['src'].data_ptr(), hin['K'].data_ptr(), hin['poses'].data_ptr()
+    h2d = hin['tgt'].numel() * 4 + hin['src'].numel() * 4 + hin['K'].numel() * 4 + hin['poses'].numel() * 4
+    d2h = 5 * 4 + hin['poses'].numel() * 4
     for s in range(4):
-        inp.disps[s], g.gdisps[s] = hp['disps'][s].data_ptr(), hp['gdisps'][s].data_ptr()
-        h2d += hp['disps'][s].numel() * 4
-        d2h += hp['gdisps'][s].numel() * 4
+        inp.disps[s] = hin['disps'][s].data_ptr()
+        h2d += hin['disps'][s].numel() * 4
+        d2h += hin['disps'][s].numel() * 4
         if exp:
-            inp.logits[s], g.glogits[s] = hp['logits'][s].data_ptr(), hp['glogits'][s].data_ptr()
-            h2d += hp['logits'][s].numel() * 4
-            d2h += hp['glogits'][s].numel() * 4
+            inp.logits[s] = hin['logits'][s].data_ptr()
+            h2d += hin['logits'][s].numel() * 4
+            d2h += hin['logits'][s].numel() * 4
+    ctxs, outs, grads = [], [], []
     try:
-        for _ in range(3):
-            L.check(lib.sfm_loss_step_host(ctx, C.byref(inp), C.c_void_p(hp['losses'].data_ptr()), C.byref(g)))
+        for k in range(n_ctx):
+            ctx = C.c_void_p()
+            L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
+            ctxs.append(ctx)
+            ho = dict(gdisps=[pin(np.empty_like(x)) for x in d['disps']], glogits=[pin(np.empty_like(x)) for x in d['logits']],
+                      gposes=pin(np.empty_like(d['poses'])), losses=pin(np.zeros(8, np.float32)))
+            g = L.SfmGrads()
+            g.gposes = ho['gposes'].data_ptr()
+            for s in range(4):
+                g.gdisps[s] = ho['gdisps'][s].data_ptr()
+                if exp:
+                    g.glogits[s] = ho['glogits'][s].data_ptr()
+            outs.append(ho)
+            grads.append(g)
+
+        def run(n):
+            for k in range(n):
+                j = k % n_ctx
+                if k >= n_ctx:
+                    L.check(lib.sfm_loss_step_host_wait(ctxs[j]))      # the step submitted n_ctx steps ago: its results are on the host
+                L.check(lib.sfm_loss_step_host_submit(ctxs[j], C.byref(inp), C.c_void_p(outs[j]['losses'].data_ptr()), C.byref(grads[j])))
+            for j in range(n_ctx):
+                L.check(lib.sfm_loss_step_host_wait(ctxs[j]))
+        run(3 * n_ctx)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            L.check(lib.sfm_loss_step_host(ctx, C.byref(inp), C.c_void_p(hp['losses'].data_ptr()), C.byref(g)))
+        run(steps)
         sec = (time.perf_counter() - t0) / steps
+        loss = float(outs[(steps - 1) % n_ctx]['losses'][0])
     finally:
-        lib.sfm_host_ctx_destroy(ctx)
-    return B * pyramid_pixels(H, W) / sec / 1e6, h2d, d2h, float(hp['losses'][0])
+        for ctx in ctxs:
+            lib.sfm_host_ctx_destroy(ctx)
+    return B * pyramid_pixels(H, W) / sec / 1e6, h2d, d2h, loss
 
 
 def run_b200(args):
@@ -457,9 +478,12 @@ def run_b200(args):
     if world == 1:
         # ---- e2e through the host-buffer C-ABI entry point
         e2e_steps = max(5, min(200, args.steps))
-        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device)
+        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device, n_ctx=2)
+        ev1, _, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=1)
         line['e2e'] = dict(value=ev, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
-                           api='sfm_loss_step_host (pinned host buffers; H2D, pyramid + fused fwd+bwd, D2H of losses and gradients)')
+                           api='sfm_loss_step_host_submit/_wait, two host contexts used alternately (pinned host buffers; every step: '
+                               'H2D of all inputs, pyramid + fused fwd+bwd, D2H of losses and all gradients)',
+                           synchronous_value=ev1, synchronous_api='sfm_loss_step_host (one step at a time)')
         # ---- other single-GPU BASELINE shapes, device timed
         if not args.no_other:
             others = {}

@@ -206,6 +206,13 @@ typedef struct SfmHostCtx SfmHostCtx;
 int sfm_host_ctx_create(const SfmDesc* desc, SfmHostCtx** ctx_out);
 int sfm_host_ctx_destroy(SfmHostCtx* ctx);
 int sfm_loss_step_host(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, const SfmGrads* grads);
+/* The same step split in two, for callers that keep several steps in flight (a data loader that prepares
+ * step k+1 while step k runs): _submit enqueues the H2D copies, the kernels and the D2H copies on the context's
+ * own stream and returns; _wait blocks until they are done.  The host buffers of a submitted step must stay
+ * valid (and, for the outputs, untouched) until _wait returns.  With two contexts used alternately the copies of
+ * one step overlap the kernels of the other (pinned memory required for the overlap). */
+int sfm_loss_step_host_submit(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, const SfmGrads* grads);
+int sfm_loss_step_host_wait(SfmHostCtx* ctx);
 
 #ifdef __cplusplus
 }

@@ -402,7 +402,18 @@ extern "C" int sfm_host_ctx_create(const SfmDesc* desc, SfmHostCtx** ctx_out) {
   return 0;
 }
 
+extern "C" int sfm_loss_step_host_wait(SfmHostCtx* c) {
+  if (!c) { sfm_set_error("sfm_loss_step_host_wait: null context"); return SFM_E_NULL_POINTER; }
+  SFM_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int sfm_loss_step_host(SfmHostCtx* c, const SfmInputs* in, float* losses_out, const SfmGrads* grads) {
+  const int rc = sfm_loss_step_host_submit(c, in, losses_out, grads);
+  return rc ? rc : sfm_loss_step_host_wait(c);
+}
+
+extern "C" int sfm_loss_step_host_submit(SfmHostCtx* c, const SfmInputs* in, float* losses_out, const SfmGrads* grads) {
   if (!c || !in || !losses_out || !grads) { sfm_set_error("sfm_loss_step_host: null pointer"); return SFM_E_NULL_POINTER; }
   const SfmDesc* d = &c->desc;
   int rc = check_inputs(d, in, true);
@@ -441,6 +452,5 @@ extern "C" int sfm_loss_step_host(SfmHostCtx* c, const SfmInputs* in, float* los
     if (m.use_exp)
       SFM_CUDA_CHECK(cudaMemcpyAsync(grads->glogits[s], c->d_glogits[s], (size_t)d->B * d->S * hw, cudaMemcpyDeviceToHost, st));
   }
-  SFM_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -69,6 +69,8 @@ SYMBOLS = {
     'sfm_host_ctx_create': (_i, [_D, C.POINTER(_vp)]),
     'sfm_host_ctx_destroy': (_i, [_vp]),
     'sfm_loss_step_host': (_i, [_vp, _I, _vp, _G]),
+    'sfm_loss_step_host_submit': (_i, [_vp, _I, _vp, _G]),
+    'sfm_loss_step_host_wait': (_i, [_vp]),
 }
 
 _lib = None

@@ -287,6 +287,60 @@ def test_host_buffer_entry_point_matches_device_path():
         np.testing.assert_array_equal(gl[s], host(g_dev['glogits'][s]))
 
 
+def test_host_submit_wait_with_two_contexts_in_flight():
+    """sfm_loss_step_host_submit / _wait: two host contexts used alternately on different inputs reproduce the
+    synchronous call bit for bit (each context owns its stream, device buffers and workspace)."""
+    import ctypes as C
+    import torch
+    from sfm_learner_chainer_b200 import lib as L
+    lib = L.load()
+    flags = FLAGSETS['v1_ssim']
+    desc = L.SfmDesc(2, 2, 64, 208, 4, 0, flags['smooth_reg'], flags['exp_reg'], flags['ssim_rate'], 0)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    data = [make_snippets(2, 2, 64, 208, seed=60 + k) for k in range(2)]
+
+    def pack(d):
+        h = dict(tgt=pin(d['tgt']), src=pin(d['src']), K=pin(d['intrinsics']), poses=pin(d['poses']),
+                 disps=[pin(x) for x in d['disps']], gd=[pin(np.zeros_like(x)) for x in d['disps']],
+                 gp=pin(np.zeros_like(d['poses'])), losses=pin(np.zeros(8, np.float32)))
+        inp, g = L.SfmInputs(), L.SfmGrads()
+        inp.tgt, inp.src, inp.intrinsics, inp.poses = h['tgt'].data_ptr(), h['src'].data_ptr(), h['K'].data_ptr(), h['poses'].data_ptr()
+        g.gposes = h['gp'].data_ptr()
+        for s in range(4):
+            inp.disps[s], g.gdisps[s] = h['disps'][s].data_ptr(), h['gd'][s].data_ptr()
+        return h, inp, g
+
+    ctxs = []
+    try:
+        for _ in range(2):
+            ctx = C.c_void_p()
+            L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
+            ctxs.append(ctx)
+        ref = []
+        for k in range(2):
+            h, inp, g = pack(data[k])
+            L.check(lib.sfm_loss_step_host(ctxs[0], C.byref(inp), C.c_void_p(h['losses'].data_ptr()), C.byref(g)))
+            ref.append((h['losses'].numpy().copy(), [x.numpy().copy() for x in h['gd']], h['gp'].numpy().copy()))
+        packs = [pack(data[k]) for k in range(2)]
+        for rep in range(6):
+            for k in range(2):
+                if rep:
+                    L.check(lib.sfm_loss_step_host_wait(ctxs[k]))
+                h, inp, g = packs[k]
+                L.check(lib.sfm_loss_step_host_submit(ctxs[k], C.byref(inp), C.c_void_p(h['losses'].data_ptr()), C.byref(g)))
+        for k in range(2):
+            L.check(lib.sfm_loss_step_host_wait(ctxs[k]))
+            h = packs[k][0]
+            np.testing.assert_array_equal(h['losses'].numpy()[:5], ref[k][0][:5])
+            np.testing.assert_array_equal(h['gp'].numpy(), ref[k][2])
+            for s in range(4):
+                np.testing.assert_array_equal(h['gd'][s].numpy(), ref[k][1][s])
+    finally:
+        for ctx in ctxs:
+            lib.sfm_host_ctx_destroy(ctx)
+    assert lib.sfm_loss_step_host_wait(None) == L.SFM_E_NULL_POINTER
+
+
 def test_torch_autograd_bridge_and_model_surface():
     """SFMLearner.__call__ surface (base_model.py:48-124) with stub nets: loss, five reports, gradients
     reaching the producers of pred_disps / pred_poses / pred_maskes."""
