@@ -174,6 +174,23 @@ int sfm_build_tables(const SfmDesc* desc, const float* poses, const float* intri
 int sfm_disp_activation(long long n, const float* x, float* disp, float* dact, void* stream);
 int sfm_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, void* stream);
 
+/* Data layer in front of the loss path, as one device gather (datasets/kitti/kitti_raw_dataset.py:12-14
+ * load_as_float_norm; datasets/kitti/kitti_raw_transformed.py:23-74 data_augmentation and :76-93
+ * get_multi_scale_intrinsics).  The caller draws the random numbers exactly as the reference does and passes
+ * them per snippet; NULL `aug` = no augmentation (validation split). */
+typedef struct SfmAugment {
+  int32_t out_h, out_w;        /* size after random scaling: int(H * y_scaling), int(W * x_scaling)  (:36-37)  */
+  int32_t off_y, off_x;        /* random crop offsets in the rescaled image                         (:49-50)  */
+  int32_t flip;                /* != 0: horizontal flip                                             (:63-65)  */
+  int32_t reserved_;
+  double x_scaling, y_scaling; /* np.random.uniform(1, 1.15, 2), used for the intrinsics            (:34-42)  */
+} SfmAugment;
+/* frames (B, 1+S, H, W, 3) uint8 HWC on the device, frame 0 of a snippet = target (imread order); K_in (B,3,3);
+ * aug: device array of B SfmAugment or NULL.  Outputs: tgt_out (B,3,H,W), src_out (B,S,3,H,W) float32 in
+ * [-1, 1]; intrinsics_out (B,n_scales,3,3) or NULL. */
+int sfm_ingest_u8(int B, int S, int H, int W, int n_scales, const uint8_t* frames, const float* K_in,
+                  const SfmAugment* aug, float* tgt_out, float* src_out, float* intrinsics_out, void* stream);
+
 /* Stage API: projective_inverse_warp(imgs, depthes, poses, K) of transform.py:156-165 on N images of
  * one resolution.  imgs (N,3,h,w) NCHW, depth (N,h*w) [the reference passes it broadcast to 3 rows],
  * poses (N,6), K (N,3,3); proj (N,3,4) / kinv (N,3,3) optional overrides (NULL = built on device).

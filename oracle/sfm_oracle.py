@@ -758,3 +758,56 @@ def sfm_loss_raw(tgt, src, intrinsics, disps_in, poses_in, logits, cfg, raw_disp
 
 def losses_vec(losses):
     return np.array([losses[k] for k in LOSS_KEYS], np.float64)
+
+
+# --------------------------------------------------------------------------------------------------
+# The data layer in front of the loss
+# --------------------------------------------------------------------------------------------------
+def load_as_float_norm(frame_hwc_u8):
+    """datasets/kitti/kitti_raw_dataset.py:12-14: imread(path).astype(float32).transpose(2, 0, 1) / (255. * 0.5) - 1."""
+    img = frame_hwc_u8.astype(np.float32).transpose(2, 0, 1)
+    return img / (255. * 0.5) - 1
+
+
+def data_augmentation(imgs, intrinsics, aug):
+    """datasets/kitti/kitti_raw_transformed.py:23-74 with the random draws supplied (`aug`: out_h, out_w, off_y,
+    off_x, flip, x_scaling, y_scaling as float64).  imgs (1+S, 3, H, W) float32, intrinsics (3,3) float32."""
+    _, _, H, W = imgs.shape
+    xs, ys = np.float64(aug['x_scaling']), np.float64(aug['y_scaling'])
+    imgs = resize_images(imgs, (aug['out_h'], aug['out_w']))                                   # :38
+    fx, fy = intrinsics[0, 0] * xs, intrinsics[1, 1] * ys                                      # :39-42 (float32 * float64)
+    cx, cy = intrinsics[0, 2] * xs, intrinsics[1, 2] * ys
+    K = np.array([[fx, 0., cx], [0., fy, cy], [0., 0., 1.]], dtype='f')                        # make_intrinsics_matrix :16-20
+    oy, ox = aug['off_y'], aug['off_x']
+    imgs = imgs[:, :, oy:oy + H, ox:ox + W]                                                    # :51
+    K = np.array([[K[0, 0], 0., K[0, 2] - ox], [0., K[1, 1], K[1, 2] - oy], [0., 0., 1.]], dtype='f')   # :52-56
+    if aug['flip']:                                                                            # :63-65
+        imgs = imgs[:, :, :, ::-1]
+        K[0, 2] = W - K[0, 2]
+    return np.ascontiguousarray(imgs), K
+
+
+def get_multi_scale_intrinsics(K, n_scales):
+    """datasets/kitti/kitti_raw_transformed.py:76-93."""
+    out = np.zeros((n_scales, 3, 3), np.float32)
+    for s in range(n_scales):
+        out[s] = np.array([[K[0, 0] / (2 ** s), 0., K[0, 2] / (2 ** s)], [0., K[1, 1] / (2 ** s), K[1, 2] / (2 ** s)],
+                           [0., 0., 1.]], dtype='f')
+    return out
+
+
+def ingest_u8(frames, K, aug=None, n_scales=4):
+    """frames (B, 1+S, H, W, 3) uint8, K (B,3,3), aug: list of B dicts or None
+    -> tgt (B,3,H,W), src (B,S,3,H,W), intrinsics (B,n_scales,3,3), as the dataset + transform hand them to the model."""
+    B, n, H, W, _ = frames.shape
+    tgt = np.zeros((B, 3, H, W), np.float32)
+    src = np.zeros((B, n - 1, 3, H, W), np.float32)
+    Ks = np.zeros((B, n_scales, 3, 3), np.float32)
+    for b in range(B):
+        imgs = np.stack([load_as_float_norm(frames[b, j]) for j in range(n)])
+        Kb = K[b].astype(np.float32)
+        if aug is not None:
+            imgs, Kb = data_augmentation(imgs, Kb, aug[b])
+        tgt[b], src[b] = imgs[0], imgs[1:]
+        Ks[b] = get_multi_scale_intrinsics(Kb, n_scales)
+    return tgt, src, Ks

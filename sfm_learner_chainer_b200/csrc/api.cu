@@ -315,6 +315,20 @@ extern "C" int sfm_build_tables(const SfmDesc* desc, const float* poses, const f
   return sfm_launch_prep(p, (cudaStream_t)stream);
 }
 
+extern "C" int sfm_ingest_u8(int B, int S, int H, int W, int n_scales, const uint8_t* frames, const float* K_in,
+                             const SfmAugment* aug, float* tgt_out, float* src_out, float* intrinsics_out, void* stream) {
+  if (B < 1 || S < 1 || S > SFM_MAX_SOURCES || n_scales < 1 || n_scales > SFM_MAX_SCALES) {
+    sfm_set_error("sfm_ingest_u8: invalid B=%d S=%d n_scales=%d", B, S, n_scales);
+    return SFM_E_INVALID_DESC;
+  }
+  if (H < 2 || W < 2 || (long long)B * (1 + S) * H * W >= (1ll << 31)) {
+    sfm_set_error("sfm_ingest_u8: invalid shape H=%d W=%d", H, W);
+    return SFM_E_INVALID_SHAPE;
+  }
+  if (!frames || !tgt_out || !src_out || (intrinsics_out && !K_in)) { sfm_set_error("sfm_ingest_u8: null pointer"); return SFM_E_NULL_POINTER; }
+  return sfm_launch_ingest_u8(B, S, H, W, n_scales, frames, K_in, aug, tgt_out, src_out, intrinsics_out, (cudaStream_t)stream);
+}
+
 extern "C" int sfm_disp_activation(long long n, const float* x, float* disp, float* dact, void* stream) {
   if (n < 0) { sfm_set_error("sfm_disp_activation: n < 0"); return SFM_E_INVALID_SHAPE; }
   if (!x || (!disp && !dact)) { sfm_set_error("sfm_disp_activation: null pointer"); return SFM_E_NULL_POINTER; }

@@ -81,3 +81,14 @@ def to_numpy(a):
     if is_cupy(a):
         return a.get()
     return np.asarray(a)
+
+
+def from_host_bytes(like, buf):
+    """Device uint8 array holding the bytes of `buf` (small parameter blocks), through the caller's allocator."""
+    raw = np.frombuffer(bytes(buf), dtype=np.uint8).copy()
+    if is_torch(like):
+        return _torch().from_numpy(raw).to(like.device)
+    if is_cupy(like):
+        import cupy
+        return cupy.asarray(raw)
+    raise TypeError('cannot allocate like %s' % type(like))

@@ -196,6 +196,54 @@ class ViewSynthesisLoss(object):
         return proj, kinv
 
 
+def draw_augmentation(H, W, rng=None):
+    """The random numbers of data_augmentation (datasets/kitti/kitti_raw_transformed.py:23-74), drawn in the
+    reference's order from `rng` (default: the global numpy RNG the reference uses): scaling pair (:34),
+    crop offsets (:49-50), flip (:64).  -> dict for ingest_u8."""
+    import numpy as np
+    rng = rng or np.random
+    scaling = rng.uniform(1, 1.15, 2)
+    x_scaling, y_scaling = scaling[0], scaling[1]
+    out_h, out_w = int(H * y_scaling), int(W * x_scaling)
+    off_y = int(rng.randint(0, out_h - H + 1))
+    off_x = int(rng.randint(0, out_w - W + 1))
+    flip = bool(rng.rand() < 0.5)
+    return dict(out_h=out_h, out_w=out_w, off_y=off_y, off_x=off_x, flip=flip, x_scaling=float(x_scaling),
+                y_scaling=float(y_scaling))
+
+
+def ingest_u8(frames, K, aug=None, n_scales=N_SCALES):
+    """Decoded uint8 frames -> what SFMLearner.__call__ receives, in one device gather:
+    load_as_float_norm (datasets/kitti/kitti_raw_dataset.py:12-14), data_augmentation and
+    get_multi_scale_intrinsics (datasets/kitti/kitti_raw_transformed.py:23-93).
+
+    frames (B, 1+S, H, W, 3) uint8 device array (frame 0 = target); K (B,3,3); aug: list of B dicts from
+    draw_augmentation, or None (no augmentation).  -> tgt (B,3,H,W), src (B,S,3,H,W), intrinsics (B,n_scales,3,3)."""
+    if len(frames.shape) != 5 or frames.shape[4] != 3:
+        raise ValueError('frames must be (B, 1+S, H, W, 3) uint8')
+    B, n, H, W, _ = [int(v) for v in frames.shape]
+    S = n - 1
+    D.check_array(frames, 'frames', (B, n, H, W, 3), 'uint8')
+    D.check_array(K, 'K', (B, 3, 3))
+    aug_dev = None
+    if aug is not None:
+        if len(aug) != B:
+            raise ValueError('aug must hold one entry per snippet')
+        arr = (L.SfmAugment * B)()
+        for b, a in enumerate(aug):
+            if not (H <= a['out_h'] and W <= a['out_w'] and 0 <= a['off_y'] <= a['out_h'] - H and 0 <= a['off_x'] <= a['out_w'] - W):
+                raise ValueError('aug[%d]: crop window outside the rescaled image' % b)
+            arr[b] = L.SfmAugment(a['out_h'], a['out_w'], a['off_y'], a['off_x'], 1 if a['flip'] else 0, 0,
+                                  a['x_scaling'], a['y_scaling'])
+        aug_dev = D.from_host_bytes(frames, arr)
+    tgt = D.empty(K, (B, 3, H, W))
+    src = D.empty(K, (B, S, 3, H, W))
+    Ks = D.empty(K, (B, n_scales, 3, 3))
+    L.check(L.load().sfm_ingest_u8(B, S, H, W, n_scales, _vp(frames), _vp(K), _vp(aug_dev), _vp(tgt), _vp(src), _vp(Ks),
+                                   C.c_void_p(D.current_stream(K))))
+    return tgt, src, Ks
+
+
 def disp_activation(x, want_dact=False):
     """DISP_SCALING * F.sigmoid(x) + MIN_DISP (models/disp_net.py:7-8,104) as a stage, with the device code
     the fused kernels inline under `raw_disp_scales`.  -> disp [, d disp / d x]."""

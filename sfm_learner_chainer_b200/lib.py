@@ -39,6 +39,11 @@ class SfmGrads(C.Structure):
     _fields_ = [('gdisps', _vp * SFM_MAX_SCALES), ('gposes', _vp), ('glogits', _vp * SFM_MAX_SCALES)]
 
 
+class SfmAugment(C.Structure):
+    _fields_ = [('out_h', C.c_int32), ('out_w', C.c_int32), ('off_y', C.c_int32), ('off_x', C.c_int32),
+                ('flip', C.c_int32), ('reserved_', C.c_int32), ('x_scaling', C.c_double), ('y_scaling', C.c_double)]
+
+
 class SfmDebug(C.Structure):
     _fields_ = [('P', _vp * SFM_MAX_SCALES), ('u0', _vp * SFM_MAX_SCALES), ('v0', _vp * SFM_MAX_SCALES),
                 ('inb', _vp * SFM_MAX_SCALES)]
@@ -59,6 +64,7 @@ SYMBOLS = {
     'sfm_pyramid': (_i, [_D, _vp, _vp, _vp, _vp]),
     'sfm_pyramid_export': (_i, [_D, _vp, _i, _vp, _vp, _vp]),
     'sfm_build_tables': (_i, [_D, _vp, _vp, _vp, _vp, _vp]),
+    'sfm_ingest_u8': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'sfm_disp_activation': (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
     'sfm_pose_reduce': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'sfm_warp_forward': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

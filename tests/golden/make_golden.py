@@ -151,6 +151,57 @@ def make_seam():
         np.savez_compressed(os.path.join(HERE, '%s.npz' % name), **blob)
 
 
+def make_ingest():
+    """The data layer in front of the loss: the reference's own load_as_float_norm
+    (datasets/kitti/kitti_raw_dataset.py:12-14) and _transform = data_augmentation + get_multi_scale_intrinsics
+    (datasets/kitti/kitti_raw_transformed.py:23-102) on synthetic uint8 frames, with the global numpy RNG seeded
+    per snippet.  The modules' unrelated imports (cv2, PIL, scipy.misc.imread, chainer.dataset(s)) are stubbed;
+    imread is the stub that hands the synthetic frame to load_as_float_norm."""
+    import types
+    frames_by_path = {}
+    for name in ('cv2', 'PIL', 'PIL.Image'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['PIL'].Image = sys.modules['PIL.Image']
+    import scipy
+    misc = types.ModuleType('scipy.misc')
+    misc.imread = lambda path: frames_by_path[path]
+    sys.modules['scipy.misc'] = misc
+    scipy.misc = misc
+    ds = types.ModuleType('chainer.datasets')
+    ds.TransformDataset = type('TransformDataset', (object,), {'__init__': lambda self, d, t: None})
+    dsm = types.ModuleType('chainer.dataset')
+    dsm.DatasetMixin = type('DatasetMixin', (object,), {})
+    sys.modules['chainer.datasets'], sys.modules['chainer.dataset'] = ds, dsm
+    chainer.datasets, chainer.dataset = ds, dsm
+    import datasets.kitti.kitti_raw_dataset as ref_ds                # reference code, unmodified
+    import datasets.kitti.kitti_raw_transformed as ref_tr
+
+    B, S, H, W = 3, 2, 32, 104
+    rs = np.random.RandomState(77)
+    lo = rs.uniform(0, 255, (B, 1 + S, H // 4, W // 4, 3))
+    frames = np.clip(np.kron(lo, np.ones((1, 1, 4, 4, 1))) + rs.uniform(-20, 20, (B, 1 + S, H, W, 3)), 0, 255).astype(np.uint8)
+    K = np.array([[[241.67 * W / 416, 0, 204.2 * W / 416], [0, 246.28 * H / 128, 59.0 * H / 128], [0, 0, 1]]] * B, np.float32)
+    K[1] *= np.array([[1.03, 1, 0.98], [1, 0.97, 1.05], [1, 1, 1]], np.float32)
+    seeds = np.array([11, 12, 14])               # 14 flips, 11 and 12 do not (checked below)
+    tgt, src, Ks, flips = [], [], [], []
+    for b in range(B):
+        for j in range(1 + S):
+            frames_by_path['f%d_%d' % (b, j)] = frames[b, j]
+        t = ref_ds.load_as_float_norm('f%d_0' % b)
+        r = [ref_ds.load_as_float_norm('f%d_%d' % (b, j)) for j in range(1, 1 + S)]
+        np.random.seed(int(seeds[b]))
+        to, so, Ko, _ = ref_tr._transform((t, r, np.copy(K[b]), np.linalg.inv(K[b])), n_scale=4)
+        tgt.append(np.asarray(to))
+        src.append(np.asarray(so))
+        Ks.append(np.stack(Ko))
+    # un-augmented path (validation split): load_as_float_norm + get_multi_scale_intrinsics only
+    plain_tgt = np.stack([ref_ds.load_as_float_norm('f%d_0' % b) for b in range(B)])
+    plain_K = np.stack([np.stack(ref_tr.get_multi_scale_intrinsics(K[b], 4)) for b in range(B)])
+    np.savez_compressed(os.path.join(HERE, 'ingest_u8.npz'), frames=frames, K=K, seeds=seeds, tgt=np.stack(tgt),
+                        src=np.stack(src), intrinsics=np.stack(Ks), plain_tgt=plain_tgt, plain_intrinsics=plain_K)
+    print('ingest_u8', np.stack(tgt).shape, np.stack(src).shape, np.stack(Ks).shape, np.stack(tgt).dtype)
+
+
 def run_warp(data, dtype, scale=0, i=0):
     """projective_inverse_warp (transform.py:156) + its stages at one scale."""
     reset_reference_caches()
@@ -189,6 +240,9 @@ def main():
     if '--seam-only' in sys.argv:
         make_seam()
         return
+    if '--ingest-only' in sys.argv:
+        make_ingest()
+        return
     for name, B, S, H, W, seed, harsh, flags in CASES:
         data = make_snippets(B, S, H, W, seed=seed, harsh=harsh, rough_disp=(seed % 2 == 1))
         blob = dict(tgt=data['tgt'], src=data['src'], intrinsics=data['intrinsics'], poses=data['poses'],
@@ -215,6 +269,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'loss_%s.npz' % name), **blob)
     np.savez_compressed(os.path.join(HERE, 'interp_sampler.npz'), **run_interp(7))
     make_seam()
+    make_ingest()
     print('golden fixtures written to', HERE)
 
 
