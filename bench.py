@@ -312,7 +312,7 @@ class Workload(object):
         return float(np.mean(ts)), float(ts[len(ts) // 2])
 
 
-def run_e2e(cfg_name, steps, device, n_ctx=2):
+def run_e2e(cfg_name, steps, device, n_ctx=2, u8=False):
     """Same metric through the host-buffer C-ABI entry point: pinned host inputs -> H2D -> pyramid + fused
     fwd+bwd -> D2H of the five losses and every gradient, EVERY step.  `n_ctx` host contexts are used alternately
     (sfm_loss_step_host_submit / _wait), the way a data loader keeps the next step's copies in flight while the
@@ -340,6 +340,18 @@ def run_e2e(cfg_name, steps, device, n_ctx=2):
             inp.logits[s] = hin['logits'][s].data_ptr()
             h2d += hin['logits'][s].numel() * 4
             d2h += hin['logits'][s].numel() * 4
+    if u8:
+        # data-layer entry: decoded uint8 frames + augmentation draws instead of float images (sfm_ingest_u8 on the device)
+        from sfm_learner_chainer_b200.functions import draw_augmentation
+        rs = np.random.RandomState(2)
+        imgs = np.concatenate([d['tgt'][:, None], d['src']], 1)
+        frames = pin(np.clip(np.round((imgs.transpose(0, 1, 3, 4, 2) + 1) * 127.5), 0, 255).astype(np.uint8))
+        K0 = pin(d['intrinsics'][:, 0].copy())
+        aug = (L.SfmAugment * B)()
+        for b in range(B):
+            a = draw_augmentation(H, W, rs)
+            aug[b] = L.SfmAugment(a['out_h'], a['out_w'], a['off_y'], a['off_x'], 1 if a['flip'] else 0, 0, a['x_scaling'], a['y_scaling'])
+        h2d += frames.numel() + K0.numel() * 4 + C.sizeof(aug) - (hin['tgt'].numel() + hin['src'].numel() + hin['K'].numel()) * 4
     ctxs, outs, grads = [], [], []
     try:
         for k in range(n_ctx):
@@ -362,7 +374,11 @@ def run_e2e(cfg_name, steps, device, n_ctx=2):
                 j = k % n_ctx
                 if k >= n_ctx:
                     L.check(lib.sfm_loss_step_host_wait(ctxs[j]))      # the step submitted n_ctx steps ago: its results are on the host
-                L.check(lib.sfm_loss_step_host_submit(ctxs[j], C.byref(inp), C.c_void_p(outs[j]['losses'].data_ptr()), C.byref(grads[j])))
+                if u8:
+                    L.check(lib.sfm_loss_step_host_u8_submit(ctxs[j], C.c_void_p(frames.data_ptr()), C.c_void_p(K0.data_ptr()), aug,
+                                                             C.byref(inp), C.c_void_p(outs[j]['losses'].data_ptr()), C.byref(grads[j])))
+                else:
+                    L.check(lib.sfm_loss_step_host_submit(ctxs[j], C.byref(inp), C.c_void_p(outs[j]['losses'].data_ptr()), C.byref(grads[j])))
             for j in range(n_ctx):
                 L.check(lib.sfm_loss_step_host_wait(ctxs[j]))
         run(3 * n_ctx)
@@ -480,10 +496,14 @@ def run_b200(args):
         e2e_steps = max(5, min(200, args.steps))
         ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device, n_ctx=2)
         ev1, _, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=1)
+        ev8, h2d8, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=2, u8=True)
         line['e2e'] = dict(value=ev, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
                            api='sfm_loss_step_host_submit/_wait, two host contexts used alternately (pinned host buffers; every step: '
                                'H2D of all inputs, pyramid + fused fwd+bwd, D2H of losses and all gradients)',
-                           synchronous_value=ev1, synchronous_api='sfm_loss_step_host (one step at a time)')
+                           synchronous_value=ev1, synchronous_api='sfm_loss_step_host (one step at a time)',
+                           u8_frames_value=ev8, u8_frames_h2d_bytes_per_step=h2d8,
+                           u8_frames_api='sfm_loss_step_host_u8_submit/_wait: decoded uint8 frames + augmentation draws in, '
+                                         'normalisation / random scale-crop-flip / multi-scale intrinsics on the device (data-layer fusion)')
         # ---- other single-GPU BASELINE shapes, device timed
         if not args.no_other:
             others = {}

@@ -231,6 +231,13 @@ int sfm_loss_step_host(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, 
 int sfm_loss_step_host_submit(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, const SfmGrads* grads);
 int sfm_loss_step_host_wait(SfmHostCtx* ctx);
 
+/* The host-buffer step fed by the data layer's raw material: `frames` (B, 1+S, H, W, 3) uint8 HWC, `K_in` (B,3,3)
+ * and `aug` (B SfmAugment or NULL) are HOST pointers; the images and intrinsics of `in` are ignored (sfm_ingest_u8
+ * produces them on the device), its disps / poses / logits are host pointers as in sfm_loss_step_host_submit.
+ * The H2D copy carries 1 byte per image sample instead of 4.  Complete with sfm_loss_step_host_wait. */
+int sfm_loss_step_host_u8_submit(SfmHostCtx* ctx, const uint8_t* frames, const float* K_in, const SfmAugment* aug,
+                                 const SfmInputs* in, float* losses_out, const SfmGrads* grads);
+
 #ifdef __cplusplus
 }
 #endif

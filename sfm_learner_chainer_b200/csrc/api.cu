@@ -354,6 +354,10 @@ struct SfmHostCtx {
   float* d_logits[SFM_MAX_SCALES];
   float* d_gdisp[SFM_MAX_SCALES];
   float* d_glogits[SFM_MAX_SCALES];
+  // uint8 entry (sfm_loss_step_host_u8_submit): allocated on first use
+  uint8_t* d_frames;
+  SfmAugment* d_aug;
+  float* d_Kin;
   std::vector<void*> allocs;
 };
 
@@ -427,18 +431,49 @@ extern "C" int sfm_loss_step_host(SfmHostCtx* c, const SfmInputs* in, float* los
   return rc ? rc : sfm_loss_step_host_wait(c);
 }
 
+static int host_submit(SfmHostCtx* c, const SfmInputs* in, float* losses_out, const SfmGrads* grads, bool images_on_device);
+
 extern "C" int sfm_loss_step_host_submit(SfmHostCtx* c, const SfmInputs* in, float* losses_out, const SfmGrads* grads) {
+  return host_submit(c, in, losses_out, grads, false);
+}
+
+extern "C" int sfm_loss_step_host_u8_submit(SfmHostCtx* c, const uint8_t* frames, const float* K_in, const SfmAugment* aug,
+                                            const SfmInputs* in, float* losses_out, const SfmGrads* grads) {
+  if (!c || !frames || !K_in || !in) { sfm_set_error("sfm_loss_step_host_u8_submit: null pointer"); return SFM_E_NULL_POINTER; }
+  const SfmDesc* d = &c->desc;
+  const size_t n_frames = (size_t)d->B * (1 + d->S) * d->H * d->W * 3;
+  if (!c->d_frames) {
+    int rc;
+    if ((rc = host_alloc(c, (void**)&c->d_frames, n_frames))) return rc;
+    if ((rc = host_alloc(c, (void**)&c->d_aug, (size_t)d->B * sizeof(SfmAugment)))) return rc;
+    if ((rc = host_alloc(c, (void**)&c->d_Kin, (size_t)d->B * 9 * sizeof(float)))) return rc;
+  }
+  cudaStream_t st = c->stream;
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_frames, frames, n_frames, cudaMemcpyHostToDevice, st));
+  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_Kin, K_in, (size_t)d->B * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (aug) SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_aug, aug, (size_t)d->B * sizeof(SfmAugment), cudaMemcpyHostToDevice, st));
+  int rc = sfm_launch_ingest_u8(d->B, d->S, d->H, d->W, d->n_scales, c->d_frames, c->d_Kin, aug ? c->d_aug : nullptr, c->d_tgt,
+                                c->d_src, c->d_K, st);
+  if (rc) return rc;
+  return host_submit(c, in, losses_out, grads, true);
+}
+
+static int host_submit(SfmHostCtx* c, const SfmInputs* in, float* losses_out, const SfmGrads* grads, bool images_on_device) {
   if (!c || !in || !losses_out || !grads) { sfm_set_error("sfm_loss_step_host: null pointer"); return SFM_E_NULL_POINTER; }
   const SfmDesc* d = &c->desc;
-  int rc = check_inputs(d, in, true);
+  SfmInputs chk = *in;
+  if (images_on_device) { chk.tgt = c->d_tgt; chk.src = c->d_src; chk.intrinsics = c->d_K; }   // produced by the ingest kernel
+  int rc = check_inputs(d, &chk, true);
   if (rc) return rc;
   if ((rc = check_grads(d, grads))) return rc;
   const Modes m = modes_of(d);
   cudaStream_t st = c->stream;
   const size_t img = (size_t)d->H * d->W * 3 * sizeof(float);
-  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_tgt, in->tgt, d->B * img, cudaMemcpyHostToDevice, st));
-  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_src, in->src, (size_t)d->B * d->S * img, cudaMemcpyHostToDevice, st));
-  SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_K, in->intrinsics, (size_t)d->B * d->n_scales * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (!images_on_device) {
+    SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_tgt, in->tgt, d->B * img, cudaMemcpyHostToDevice, st));
+    SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_src, in->src, (size_t)d->B * d->S * img, cudaMemcpyHostToDevice, st));
+    SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_K, in->intrinsics, (size_t)d->B * d->n_scales * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
   const size_t pose_bytes = (size_t)d->B * d->S * 6 * (d->raw_pose_hw > 0 ? d->raw_pose_hw : 1) * sizeof(float);
   SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_poses, in->poses, pose_bytes, cudaMemcpyHostToDevice, st));
   SfmInputs din{};

@@ -77,6 +77,7 @@ SYMBOLS = {
     'sfm_loss_step_host': (_i, [_vp, _I, _vp, _G]),
     'sfm_loss_step_host_submit': (_i, [_vp, _I, _vp, _G]),
     'sfm_loss_step_host_wait': (_i, [_vp]),
+    'sfm_loss_step_host_u8_submit': (_i, [_vp, _vp, _vp, _vp, _I, _vp, _G]),
 }
 
 _lib = None

@@ -73,3 +73,47 @@ def test_ingest_argument_errors():
         ingest_u8(frames, K)                                    # host arrays: no CPU fallback
     with pytest.raises(ValueError):
         ingest_u8(to_dev(frames), to_dev(K), [dict(out_h=16, out_w=16, off_y=1, off_x=0, flip=False, x_scaling=1.0, y_scaling=1.0)])
+
+
+def test_host_u8_entry_point_matches_device_path():
+    """sfm_loss_step_host_u8_submit (host uint8 frames in) == ingest_u8 + forward_backward on the device."""
+    import ctypes as C
+    import torch
+    from sfm_learner_chainer_b200 import ingest_u8, ViewSynthesisLoss, lib as L
+    from sfm_learner_chainer_b200.synthetic import make_snippets
+    B, S, H, W = 2, 2, 64, 208
+    d = make_snippets(B, S, H, W, seed=71)
+    rs = np.random.RandomState(71)
+    frames = rs.randint(0, 256, (B, 1 + S, H, W, 3)).astype(np.uint8)
+    K = np.ascontiguousarray(d['intrinsics'][:, 0])
+    aug = [draw_augmentation(H, W, rs) for _ in range(B)]
+    flags = dict(smooth_reg=0.1, exp_reg=0.2, ssim_rate=0.0)
+    tgt, src, Ks = ingest_u8(to_dev(frames), to_dev(K), aug)
+    l_dev, g_dev = ViewSynthesisLoss(**flags).forward_backward(tgt, src, Ks, [to_dev(x) for x in d['disps']], to_dev(d['poses']),
+                                                               [to_dev(x) for x in d['logits']])
+    lib = L.load()
+    desc = L.SfmDesc(B, S, H, W, 4, 0, flags['smooth_reg'], flags['exp_reg'], flags['ssim_rate'], 0)
+    ctx = C.c_void_p()
+    L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
+    try:
+        arr = (L.SfmAugment * B)(*[L.SfmAugment(a['out_h'], a['out_w'], a['off_y'], a['off_x'], int(a['flip']), 0, a['x_scaling'], a['y_scaling']) for a in aug])
+        inp, grads = L.SfmInputs(), L.SfmGrads()
+        inp.poses = d['poses'].ctypes.data
+        gd = [np.empty_like(x) for x in d['disps']]
+        gl = [np.empty_like(x) for x in d['logits']]
+        gp = np.empty_like(d['poses'])
+        for s in range(4):
+            inp.disps[s], inp.logits[s] = d['disps'][s].ctypes.data, d['logits'][s].ctypes.data
+            grads.gdisps[s], grads.glogits[s] = gd[s].ctypes.data, gl[s].ctypes.data
+        grads.gposes = gp.ctypes.data
+        losses = np.empty(5, np.float32)
+        for _ in range(2):
+            L.check(lib.sfm_loss_step_host_u8_submit(ctx, frames.ctypes.data, K.ctypes.data, arr, C.byref(inp), losses.ctypes.data, C.byref(grads)))
+            L.check(lib.sfm_loss_step_host_wait(ctx))
+    finally:
+        lib.sfm_host_ctx_destroy(ctx)
+    np.testing.assert_array_equal(losses, host(l_dev))
+    np.testing.assert_array_equal(gp, host(g_dev['gposes']))
+    for s in range(4):
+        np.testing.assert_array_equal(gd[s], host(g_dev['gdisps'][s]))
+        np.testing.assert_array_equal(gl[s], host(g_dev['glogits'][s]))
