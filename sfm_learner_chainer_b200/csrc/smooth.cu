@@ -31,7 +31,17 @@ __device__ __forceinline__ float sgnc(float v, float c) {   // sign(v) * c (c > 
 template <bool GRAD>
 __global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ SfmFusedParams p) {
   const int lane = threadIdx.x;
+  // No early cudaTriggerProgrammaticLaunchCompletion() here (the implicit trigger at CTA exit is used): the
+  // dependent fused kernel has at most 12-20 single-warp CTAs per SM, and when its CTAs are dispatched while this
+  // grid and the pyramid grid still occupy part of the chip they pile up on the SMs that happen to be free.  For
+  // grids below one wave that imbalance sets the kernel time (measured at cfg2: step 58.6 us with the early
+  // trigger vs 49.1 us without, same kernels).
+#ifndef SFM_SMOOTH_TRIGGER
+#define SFM_SMOOTH_TRIGGER 0
+#endif
+#if SFM_SMOOTH_TRIGGER
   cudaTriggerProgrammaticLaunchCompletion();
+#endif
   // ---- task decode (uniform): strips x row segments of every (snippet, scale)
   int t = blockIdx.x, s = 0;
 #pragma unroll

@@ -420,12 +420,30 @@ static int launch_ssim_kernel(K kernel, const SfmFusedParams& p, cudaStream_t st
 int launch_epilogue(const SfmFusedParams& p, cudaStream_t stream);
 
 static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug, long long want_warps, cudaStream_t stream) {
+  // Task height (rows per strip segment).  Cost model, calibrated on B200 (tools/time_graph.py sweeps):
+  // a task marches 3*ceil((hseg+4)/3) rows per source (4 halo rows, row loop unrolled by three); up to
+  // SFM_MINB_SSIM single-warp CTAs are resident per SM, i.e. 3 per scheduler.  Above one wave the time is
+  // waves x rows; below one wave the busiest scheduler holds w = ceil(tasks / schedulers) warps and runs them at
+  // a relative issue efficiency of 0.66 / 0.9 / 1.0 for w = 1 / 2 / 3 (a lone warp cannot hide its own latencies).
+  // Example cfg2 (B=4, 128x416): hseg 8 -> 1296 tasks, w=3, 12 rows: 36.8 us; hseg 11 -> 976 tasks, w=2, 15 rows: 33.4 us.
+  (void)want_warps;
   int hseg = 64;
-  for (;;) {
-    long long n = 0;
-    for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + hseg - 1) / hseg);
-    if (n >= want_warps || hseg <= 8) break;
-    hseg >>= 1;
+  {
+    const long long sched = (long long)g_num_sms * 4, slots = (long long)g_num_sms * SFM_MINB_SSIM;
+    double best = 1e300;
+    for (int h = 8; h <= 64; ++h) {
+      long long n = 0;
+      for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + h - 1) / h);
+      const double rows = 3.0 * ((h + 4 + 2) / 3);
+      double cost;
+      if (n > slots) {
+        cost = rows * 3.0 * (double)((n + slots - 1) / slots);
+      } else {
+        const long long w = (n + sched - 1) / sched;
+        cost = rows * (double)w / (w <= 1 ? 0.66 : w == 2 ? 0.9 : 1.0);
+      }
+      if (cost <= best) { best = cost; hseg = h; }
+    }
   }
   {
     const char* e = getenv("SFM_HSEG");          // development knob
