@@ -23,6 +23,7 @@ function by function after the reference (citations are relative to
 * ``models/base_model.py:126-142`` compute_ssim
 * ``models/base_model.py:157-167`` compute_exp_reg_loss
 * ``models/base_model.py:169-185`` compute_smooth_loss
+* ``models/base_model.py:144-155`` compute_disp_smooth (edge-aware alternative, commented out at :78-80)
 * ``models/disp_net.py:7-8,104``  disparity activation  (seam)
 * ``models/pose_net.py:52-53``    pose scaling / spatial mean (seam)
 
@@ -489,9 +490,23 @@ def projective_inverse_warp(imgs, depth, poses, K, proj=None, Kinv=None):
 # --------------------------------------------------------------------------
 # the full loss path, forward + analytic backward
 # --------------------------------------------------------------------------
+def disp_smooth_terms(img, D):
+    """compute_disp_smooth (base_model.py:144-155): first differences of the disparity weighted by
+    exp(-|channel-mean image gradient|).  img (B,3,h,w), D (B,1,h,w) -> (d_dx, e_x, d_dy, e_y)."""
+    t = D.dtype.type
+    d_dy = D[:, :, 1:] - D[:, :, :-1]
+    d_dx = D[:, :, :, 1:] - D[:, :, :, :-1]
+    i_dy = (img[:, :, 1:] - img[:, :, :-1]).mean(axis=1, keepdims=True, dtype=D.dtype)
+    i_dx = (img[:, :, :, 1:] - img[:, :, :, :-1]).mean(axis=1, keepdims=True, dtype=D.dtype)
+    return d_dx, np.exp(-np.abs(i_dx)).astype(D.dtype), d_dy, np.exp(-np.abs(i_dy)).astype(D.dtype)
+
+
 class LossConfig(object):
     def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0,
-                 n_scales=N_SCALES, B_global=None):
+                 n_scales=N_SCALES, B_global=None, edge_aware_smooth=False):
+        # edge_aware_smooth: the smoothness term is compute_disp_smooth(curr_tgt_img, pred_disps[ns]) -- the
+        # alternative the reference keeps commented out at base_model.py:78-80 -- instead of compute_smooth_loss
+        self.edge_aware_smooth = edge_aware_smooth
         self.smooth_reg = smooth_reg
         self.exp_reg = exp_reg
         self.ssim_rate = ssim_rate
@@ -566,8 +581,22 @@ def sfm_loss(tgt, src, intrinsics, disps, poses, logits, cfg,
             debug['tgt_pyr'].append(cur_tgt)
             debug['src_pyr'].append(cur_src.reshape(B, S, 3, h, w))
         D = disps[ns]
+        # ---- edge-aware smoothness (base_model.py:78-80 as written in the comment, 144-155)
+        if use_smooth and cfg.edge_aware_smooth:
+            wgt = cfg.smooth_reg / (2 ** ns)
+            d_dx, e_x, d_dy, e_y = disp_smooth_terms(cur_tgt, D)
+            n_x, n_y = Bg * h * (w - 1), Bg * (h - 1) * w
+            smooth_loss += wgt * (_fsum(np.abs(d_dx) * e_x) / n_x + _fsum(np.abs(d_dy) * e_y) / n_y)
+            if want_grads:
+                g = gdisp[ns][:, 0]
+                sx = np.sign(d_dx[:, 0]).astype(np.float64) * e_x[:, 0] * (wgt / n_x)
+                g[:, :, 1:] += sx
+                g[:, :, :-1] -= sx
+                sy = np.sign(d_dy[:, 0]).astype(np.float64) * e_y[:, 0] * (wgt / n_y)
+                g[:, 1:, :] += sy
+                g[:, :-1, :] -= sy
         # ---- smoothness (base_model.py:75-77, 169-185)
-        if use_smooth:
+        elif use_smooth:
             wgt = cfg.smooth_reg / (2 ** ns)
             dx2, dxdy, dydx, dy2 = smooth_terms(D)
             n_dx2 = Bg * h * (w - 2)

@@ -33,7 +33,8 @@ class SFMLearner(object):
         # raw_disp_scales / raw_pose: the nets stop one op early and the kernels apply the disparity activation
         # (disp_net.py:104) / the 0.01 * spatial mean (pose_net.py:52) themselves (ViewSynthesisLoss docstring)
         self.loss_op = ViewSynthesisLoss(self.smooth_reg, self.exp_reg, self.ssim_rate, B_global=B_global,
-                                         raw_disp_scales=raw_disp_scales, raw_pose=raw_pose)
+                                         raw_disp_scales=raw_disp_scales, raw_pose=raw_pose,
+                                         edge_aware_smooth=bool(parse_dict(config, 'edge_aware_smooth', False)))
 
     def __call__(self, tgt_img, src_imgs, intrinsics, inv_intrinsics=None):
         batchsize, n_sources, _, H, W = src_imgs.shape

@@ -197,6 +197,8 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
     p.sm_dx2[s] = (float)(wgt / (Bg * h * (w - 2)));
     p.sm_mix[s] = (float)(wgt / (Bg * (h - 1) * (w - 1)));
     p.sm_dy2[s] = (float)(wgt / (Bg * (h - 2) * w));
+    p.sm_ex[s] = (float)(wgt / (Bg * h * (w - 1)));
+    p.sm_ey[s] = (float)(wgt / (Bg * (h - 1) * w));
     if (dbg) {
       p.dbg_P[s] = dbg->P[s]; p.dbg_u0[s] = dbg->u0[s]; p.dbg_v0[s] = dbg->v0[s]; p.dbg_inb[s] = dbg->inb[s];
     }
@@ -217,6 +219,7 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   p.exp_reg = m.use_exp ? d->exp_reg : 0.f;
   p.ssim_rate = d->ssim_rate;     // enters `total` even when the SSIM term itself is skipped (base_model.py:117)
   p.use_smooth = m.use_smooth ? 1 : 0;
+  p.edge_smooth = (d->flags & SFM_FLAG_EDGE_AWARE_SMOOTH) ? 1 : 0;
   int mode = 0;
   if (m.use_exp) mode |= SFM_MODE_EXP;
   if (m.use_ssim) mode |= SFM_MODE_SSIM;

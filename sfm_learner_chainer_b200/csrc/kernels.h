@@ -72,6 +72,9 @@ struct SfmFusedParams {
   float sm_dx2[SFM_MAX_SCALES];      // smooth_reg/2^s / (Bg*h*(w-2))
   float sm_mix[SFM_MAX_SCALES];      // smooth_reg/2^s / (Bg*(h-1)*(w-1))
   float sm_dy2[SFM_MAX_SCALES];      // smooth_reg/2^s / (Bg*(h-2)*w)
+  float sm_ex[SFM_MAX_SCALES];       // smooth_reg/2^s / (Bg*h*(w-1))      edge-aware variant (compute_disp_smooth)
+  float sm_ey[SFM_MAX_SCALES];       // smooth_reg/2^s / (Bg*(h-1)*w)
+  int edge_smooth;                   // SFM_FLAG_EDGE_AWARE_SMOOTH
   float smooth_reg, exp_reg, ssim_rate;
   int use_smooth;
   // debug dumps (nullptr when unused)

@@ -127,11 +127,91 @@ __global__ void __launch_bounds__(32) sfm_smooth_kernel(const __grid_constant__ 
   if (lane == 0 && loss != 0.f) atomicAdd(p.acc + 1, (double)loss);
 }
 
+// Edge-aware first-order smoothness, compute_disp_smooth (base_model.py:144-155; the alternative the reference
+// keeps commented out at its call site, :78-80; SfmDesc flag SFM_FLAG_EDGE_AWARE_SMOOTH):
+//   loss_s = smooth_reg/2^s * ( mean(|d_dx| * exp(-|mean_c i_dx|)) + mean(|d_dy| * exp(-|mean_c i_dy|)) )
+// with d = disparity, i = target image of the scale (the pyramid level, no gradient).  One thread per pixel in
+// gather form: its right / down differences give the loss terms it owns, and together with the left / up ones
+// the gradient, so there is no scatter and no atomic on gdisp.  Needs the pyramid, so unlike the second-order
+// kernel above it starts after the prep kernel.
+template <bool GRAD>
+__global__ void __launch_bounds__(256) sfm_edge_smooth_kernel(const __grid_constant__ SfmFusedParams p) {
+  const int s = blockIdx.y % p.ns, b = blockIdx.y / p.ns;
+  const int h = p.h[s], w = p.w[s], plane = h * w;
+  const bool raw = (p.raw_disp_mask >> s) & 1u;
+  const float* __restrict__ D = p.disp[s] + (size_t)b * plane;
+  const float4* __restrict__ T = p.tgt_pyr[s] + (size_t)b * plane;
+  float* __restrict__ G = GRAD ? p.gdisp[s] + (size_t)b * plane : nullptr;
+  const float kx = p.sm_ex[s], ky = p.sm_ey[s];
+  const float gyv = (GRAD && p.gy) ? __ldg(p.gy) : 1.f;
+  cudaGridDependencySynchronize();          // pyramid and loss cells (prep kernel)
+  auto disp_at = [&](int i, float& f) {
+    const float v = __ldg(D + i);
+    f = 1.f;
+    return raw ? sfm_disp_act(v, f) : v;
+  };
+  // exp(-|mean_c (b - a)|): F.mean over the three channels = ((d0 + d1) + d2) / 3, F.absolute, F.exp
+  auto edge = [&](const float4& a, const float4& c) {
+    const float m = __fdiv_rn(__fadd_rn(__fadd_rn(__fsub_rn(c.x, a.x), __fsub_rn(c.y, a.y)), __fsub_rn(c.z, a.z)), 3.f);
+    return expf(-fabsf(m));
+  };
+  float loss = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float f0, fd;
+    const float d0 = disp_at(i, f0);
+    const float4 t0 = __ldg(T + i);
+    float g = 0.f;
+    if (x + 1 < w) {
+      const float dd = __fsub_rn(disp_at(i + 1, fd), d0), e = edge(t0, __ldg(T + i + 1));
+      loss += fabsf(dd) * e * kx;
+      g -= sgnc(dd, kx) * e;
+    }
+    if (y + 1 < h) {
+      const float dd = __fsub_rn(disp_at(i + w, fd), d0), e = edge(t0, __ldg(T + i + w));
+      loss += fabsf(dd) * e * ky;
+      g -= sgnc(dd, ky) * e;
+    }
+    if (GRAD) {
+      if (x > 0) g += sgnc(__fsub_rn(d0, disp_at(i - 1, fd)), kx) * edge(__ldg(T + i - 1), t0);
+      if (y > 0) g += sgnc(__fsub_rn(d0, disp_at(i - w, fd)), ky) * edge(__ldg(T + i - w), t0);
+      G[i] = raw ? (gyv * g) * f0 : gyv * g;
+    }
+  }
+  __shared__ float part[8];
+  loss = sfm_warp_sum(loss);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    if (t != 0.f) atomicAdd(p.acc + 1, (double)t);
+  }
+}
+
 }  // namespace
+
+int sfm_launch_edge_smooth(SfmFusedParams& p, int grad, cudaStream_t stream) {
+  const int per = (p.h[0] * p.w[0] + 255) / 256;
+  dim3 grid((unsigned)(per > 32 ? 32 : per), (unsigned)(p.B * p.ns));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = sfm_pdl_enabled() ? attr : nullptr;
+  cfg.numAttrs = sfm_pdl_enabled() ? 1 : 0;
+  if (grad) SFM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sfm_edge_smooth_kernel<true>, p));
+  else SFM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sfm_edge_smooth_kernel<false>, p));
+  return 0;
+}
 
 // Fills the strip decomposition (tiles_x = strips, tiles_y = row segments, tile_begin) of `p` and launches.
 // With grad != 0 every gdisp[s] is fully written.
 int sfm_launch_smooth(SfmFusedParams& p, int grad, cudaStream_t stream) {
+  if (p.edge_smooth) return sfm_launch_edge_smooth(p, grad, stream);
   // segment height: enough warps to cover the chip a few times, few enough that the 4 extra rows stay cheap
   long long strips = 0;
   for (int s = 0; s < p.ns; ++s) strips += (long long)p.B * ((p.w[s] + SM_IW - 1) / SM_IW);

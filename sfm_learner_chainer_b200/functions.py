@@ -26,7 +26,9 @@ class ViewSynthesisLoss(object):
     """
 
     def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, n_scales=N_SCALES, B_global=None,
-                 raw_disp_scales=0, raw_pose=False):
+                 raw_disp_scales=0, raw_pose=False, edge_aware_smooth=False):
+        # edge_aware_smooth: smoothness term = compute_disp_smooth (base_model.py:144-155, commented out at :78-80)
+        self.edge_aware_smooth = bool(edge_aware_smooth)
         self.raw_disp_scales = int(raw_disp_scales)
         self.raw_pose = bool(raw_pose)
         self.smooth_reg = float(smooth_reg or 0.0)
@@ -43,6 +45,8 @@ class ViewSynthesisLoss(object):
         return self.exp_reg != 0.0
 
     def _desc(self, B, S, H, W, flags=0, raw_pose_hw=0):
+        if self.edge_aware_smooth:
+            flags |= L.SFM_FLAG_EDGE_AWARE_SMOOTH
         return L.SfmDesc(B, S, H, W, self.n_scales, int(self.B_global or 0), self.smooth_reg, self.exp_reg,
                          self.ssim_rate, flags, self.raw_disp_scales, raw_pose_hw)
 

@@ -11,6 +11,7 @@ SFM_MAX_SOURCES = 8
 SFM_FLAG_TABLES_PROVIDED = 0x1
 SFM_FLAG_REUSE_PYRAMID = 0x2
 SFM_FLAG_NO_TMA = 0x4
+SFM_FLAG_EDGE_AWARE_SMOOTH = 0x8
 
 SFM_E_INVALID_DESC = -1
 SFM_E_INVALID_SHAPE = -2

@@ -151,6 +151,31 @@ def make_seam():
         np.savez_compressed(os.path.join(HERE, '%s.npz' % name), **blob)
 
 
+def make_edge_smooth():
+    """compute_disp_smooth (base_model.py:144-155), the edge-aware smoothness the reference keeps commented out at
+    its call site (:78-80): the reference's own method on the pyramid levels, weighted as that comment writes it,
+    value and gradient w.r.t. the disparities (float64 and float32)."""
+    F = chainer.functions
+    B, S, H, W = 2, 2, 32, 104
+    data = make_snippets(B, S, H, W, seed=8, rough_disp=True)
+    flags = dict(smooth_reg=0.1, exp_reg=0.0, seq_len=3)
+    model = ref_base_model.SFMLearner(flags, {'download': None, 'path': None})
+    blob = dict(tgt=data['tgt'], smooth_reg=np.float64(flags['smooth_reg']))
+    for tag, dtype in (('f64', np.float64), ('f32', np.float32)):
+        disps = [Variable(np.ascontiguousarray(d.astype(dtype))) for d in data['disps']]
+        loss = 0
+        for ns in range(4):
+            cur = F.resize_images(data['tgt'].astype(dtype), (H // 2 ** ns, W // 2 ** ns)).data
+            loss += (flags['smooth_reg'] / (2 ** ns)) * model.compute_disp_smooth(cur, disps[ns])
+        loss.backward()
+        blob['loss_' + tag] = np.float64(loss.data)
+        for ns in range(4):
+            blob['disp%d' % ns] = data['disps'][ns]
+            blob['gdisp%d_%s' % (ns, tag)] = disps[ns].grad
+        print('edge_smooth', tag, float(loss.data))
+    np.savez_compressed(os.path.join(HERE, 'edge_smooth.npz'), **blob)
+
+
 def make_ingest():
     """The data layer in front of the loss: the reference's own load_as_float_norm
     (datasets/kitti/kitti_raw_dataset.py:12-14) and _transform = data_augmentation + get_multi_scale_intrinsics
@@ -240,6 +265,9 @@ def main():
     if '--seam-only' in sys.argv:
         make_seam()
         return
+    if '--edge-only' in sys.argv:
+        make_edge_smooth()
+        return
     if '--ingest-only' in sys.argv:
         make_ingest()
         return
@@ -270,6 +298,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'interp_sampler.npz'), **run_interp(7))
     make_seam()
     make_ingest()
+    make_edge_smooth()
     print('golden fixtures written to', HERE)
 
 
