@@ -10,8 +10,10 @@ timeout 900 python bench.py > gpurun_out/${tag}_bench_cfg2.json 2> gpurun_out/${
 cat gpurun_out/${tag}_bench_cfg2.json
 timeout 300 python bench.py --impl reference --steps 5 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench_cfg2.err
 cat gpurun_out/${tag}_bench_reference.json
-timeout 300 python tools/time_kernels.py cfg1 cfg2 cfg4 cfg5 > gpurun_out/${tag}_time_kernels.log 2>&1
+timeout 300 python tools/time_graph.py cfg1 cfg2 cfg4 cfg5 > gpurun_out/${tag}_time_kernels.log 2>&1
 cat gpurun_out/${tag}_time_kernels.log
+timeout 300 python tools/time_cfg3.py 2>/dev/null | grep cfg3 > gpurun_out/${tag}_time_cfg3.log
+cat gpurun_out/${tag}_time_cfg3.log
 kill $SMI
 # launch list of the bench command itself (graph replay is opaque to ncu's per-kernel list -> direct calls)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_cfg2.csv \
