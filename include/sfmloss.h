@@ -194,6 +194,17 @@ typedef struct SfmAugment {
 int sfm_ingest_u8(int B, int S, int H, int W, int n_scales, const uint8_t* frames, const float* K_in,
                   const SfmAugment* aug, float* tgt_out, float* src_out, float* intrinsics_out, void* stream);
 
+/* Inference-side depth evaluation of one batch (evaluate.py:94-103 + kitti_eval/depth_util.py:6-22), on the
+ * device: pred_depth (B,1,h,w) is resized to the ground truth's (Hg,Wg) (F.resize_images), clipped to
+ * [min_depth, max_depth], masked, scaled by median(gt)/median(pred) (exact medians) and compared.
+ * gt_depth (B,Hg,Wg) float32, mask (B,Hg,Wg) uint8 (non-zero = valid; masked depths must be positive).
+ * errors_out: device float[8] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3 (depth_util.py:22) and the scale
+ * factor.  scratch: sfm_eval_depth_scratch_bytes(B,Hg,Wg) bytes of device memory.  Asynchronous on `stream`. */
+size_t sfm_eval_depth_scratch_bytes(int B, int Hg, int Wg);
+int sfm_eval_depth(int B, int h, int w, int Hg, int Wg, const float* pred_depth, const float* gt_depth,
+                   const uint8_t* mask, float min_depth, float max_depth, float* errors_out, void* scratch,
+                   void* stream);
+
 /* Stage API: projective_inverse_warp(imgs, depthes, poses, K) of transform.py:156-165 on N images of
  * one resolution.  imgs (N,3,h,w) NCHW, depth (N,h*w) [the reference passes it broadcast to 3 rows],
  * poses (N,6), K (N,3,3); proj (N,3,4) / kinv (N,3,3) optional overrides (NULL = built on device).

@@ -840,3 +840,31 @@ def ingest_u8(frames, K, aug=None, n_scales=4):
         tgt[b], src[b] = imgs[0], imgs[1:]
         Ks[b] = get_multi_scale_intrinsics(Kb, n_scales)
     return tgt, src, Ks
+
+
+# --------------------------------------------------------------------------------------------------
+# Inference-side depth evaluation
+# --------------------------------------------------------------------------------------------------
+def compute_depth_errors(gt, pred):
+    """kitti_eval/depth_util.py:6-22."""
+    thresh = np.maximum((gt / pred), (pred / gt))
+    a1 = (thresh < 1.25).mean()
+    a2 = (thresh < 1.25 ** 2).mean()
+    a3 = (thresh < 1.25 ** 3).mean()
+    rmse = np.sqrt(((gt - pred) ** 2).mean())
+    rmse_log = np.sqrt(((np.log(gt) - np.log(pred)) ** 2).mean())
+    abs_rel = np.mean(np.abs(gt - pred) / gt)
+    sq_rel = np.mean(((gt - pred) ** 2) / gt)
+    return np.array([abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3], dtype='f')
+
+
+def evaluate_depth_batch(pred_depth, gt_depth, mask, min_depth, max_depth):
+    """One iteration of evaluate_depth's loop, evaluate.py:94-103: resize the prediction (B,1,h,w) to the ground
+    truth's size, clip, mask, scale by the ratio of medians, compute the seven errors.  -> (errors (7,), scale)."""
+    pred = resize_images(pred_depth, gt_depth.shape[1:])
+    pred = np.clip(pred, pred.dtype.type(min_depth), pred.dtype.type(max_depth))[:, 0]
+    m = mask.astype(bool)
+    pred, gt = pred[m], gt_depth[m]
+    scale = np.median(gt) / np.median(pred)
+    pred = pred * scale
+    return compute_depth_errors(gt, pred), scale

@@ -9,9 +9,9 @@ All arithmetic runs in hand-written sm_100a kernels behind the C ABI of include/
 from . import lib
 from .functions import (ViewSynthesisLoss, projective_inverse_warp, projective_inverse_warp_backward,
                         spatial_transformer_sampler_interp, SpatialTransformerSamplerInterp,
-                        disp_activation, pose_reduce, ingest_u8, draw_augmentation)
+                        disp_activation, pose_reduce, ingest_u8, draw_augmentation, evaluate_depth_batch)
 from .base_model import SFMLearner
 
 __all__ = ['lib', 'ViewSynthesisLoss', 'projective_inverse_warp', 'projective_inverse_warp_backward',
            'spatial_transformer_sampler_interp', 'SpatialTransformerSamplerInterp', 'SFMLearner',
-           'disp_activation', 'pose_reduce', 'ingest_u8', 'draw_augmentation']
+           'disp_activation', 'pose_reduce', 'ingest_u8', 'draw_augmentation', 'evaluate_depth_batch']

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsfmloss.so')
-SOURCES = ['api.cu', 'prep.cu', 'smooth.cu', 'fused_loss.cu', 'stage.cu', 'ingest.cu']
+SOURCES = ['api.cu', 'prep.cu', 'smooth.cu', 'fused_loss.cu', 'stage.cu', 'ingest.cu', 'eval.cu']
 HEADERS = ['common.cuh', 'kernels.h', 'ssim_march.cuh', os.path.join(ROOT, 'include', 'sfmloss.h')]
 
 

@@ -332,6 +332,20 @@ extern "C" int sfm_ingest_u8(int B, int S, int H, int W, int n_scales, const uin
   return sfm_launch_ingest_u8(B, S, H, W, n_scales, frames, K_in, aug, tgt_out, src_out, intrinsics_out, (cudaStream_t)stream);
 }
 
+extern "C" size_t sfm_eval_depth_scratch_bytes(int B, int Hg, int Wg) {
+  if (B < 1 || Hg < 1 || Wg < 1) return 0;
+  return sfm_eval_scratch_bytes_impl(B, Hg, Wg);
+}
+
+extern "C" int sfm_eval_depth(int B, int h, int w, int Hg, int Wg, const float* pred_depth, const float* gt_depth,
+                              const uint8_t* mask, float min_depth, float max_depth, float* errors_out, void* scratch,
+                              void* stream) {
+  if (B < 1 || h < 2 || w < 2 || Hg < 1 || Wg < 1) { sfm_set_error("sfm_eval_depth: invalid shape B=%d %dx%d -> %dx%d", B, h, w, Hg, Wg); return SFM_E_INVALID_SHAPE; }
+  if (!(min_depth > 0.f) || !(max_depth >= min_depth)) { sfm_set_error("sfm_eval_depth: need 0 < min_depth <= max_depth"); return SFM_E_INVALID_DESC; }
+  if (!pred_depth || !gt_depth || !mask || !errors_out || !scratch) { sfm_set_error("sfm_eval_depth: null pointer"); return SFM_E_NULL_POINTER; }
+  return sfm_launch_eval_depth(B, h, w, Hg, Wg, pred_depth, gt_depth, mask, min_depth, max_depth, errors_out, scratch, (cudaStream_t)stream);
+}
+
 extern "C" int sfm_disp_activation(long long n, const float* x, float* disp, float* dact, void* stream) {
   if (n < 0) { sfm_set_error("sfm_disp_activation: n < 0"); return SFM_E_INVALID_SHAPE; }
   if (!x || (!disp && !dact)) { sfm_set_error("sfm_disp_activation: null pointer"); return SFM_E_NULL_POINTER; }

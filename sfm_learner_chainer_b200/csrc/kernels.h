@@ -31,6 +31,9 @@ struct SfmPrepParams {
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
 int sfm_launch_ingest_u8(int B, int S, int H, int W, int ns, const uint8_t* frames, const float* K_in, const SfmAugment* aug,
                          float* tgt, float* src, float* K_out, cudaStream_t stream);   // ingest.cu
+size_t sfm_eval_scratch_bytes_impl(int B, int Hg, int Wg);                                  // eval.cu
+int sfm_launch_eval_depth(int B, int h, int w, int Hg, int Wg, const float* pred, const float* gt, const uint8_t* mask, float lo,
+                          float hi, float* out, void* scratch, cudaStream_t stream);
 int sfm_launch_disp_activation(long long n, const float* x, float* disp, float* dact, cudaStream_t stream);
 int sfm_launch_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, cudaStream_t stream);
 int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int h, int w, int padded, cudaStream_t stream);

@@ -248,6 +248,24 @@ def ingest_u8(frames, K, aug=None, n_scales=N_SCALES):
     return tgt, src, Ks
 
 
+def evaluate_depth_batch(pred_depth, gt_depth, mask, min_depth, max_depth):
+    """One iteration of evaluate_depth's loop (evaluate.py:94-103) + compute_depth_errors
+    (kitti_eval/depth_util.py:6-22) on the device: pred_depth (B,1,h,w), gt_depth (B,Hg,Wg), mask (B,Hg,Wg) uint8.
+    -> device float array (8,): abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, scale_factor."""
+    B, _, h, w = [int(v) for v in pred_depth.shape]
+    Hg, Wg = int(gt_depth.shape[1]), int(gt_depth.shape[2])
+    D.check_array(pred_depth, 'pred_depth', (B, 1, h, w))
+    D.check_array(gt_depth, 'gt_depth', (B, Hg, Wg))
+    D.check_array(mask, 'mask', (B, Hg, Wg), 'uint8')
+    lib = L.load()
+    scratch = D.empty(pred_depth, (lib.sfm_eval_depth_scratch_bytes(B, Hg, Wg) + 256,), 'uint8')
+    sp = C.c_void_p((D.ptr(scratch) + 255) // 256 * 256)
+    out = D.empty(pred_depth, (8,))
+    L.check(lib.sfm_eval_depth(B, h, w, Hg, Wg, _vp(pred_depth), _vp(gt_depth), _vp(mask), float(min_depth), float(max_depth),
+                               _vp(out), sp, C.c_void_p(D.current_stream(pred_depth))))
+    return out
+
+
 def disp_activation(x, want_dact=False):
     """DISP_SCALING * F.sigmoid(x) + MIN_DISP (models/disp_net.py:7-8,104) as a stage, with the device code
     the fused kernels inline under `raw_disp_scales`.  -> disp [, d disp / d x]."""

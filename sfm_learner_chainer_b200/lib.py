@@ -66,6 +66,8 @@ SYMBOLS = {
     'sfm_pyramid_export': (_i, [_D, _vp, _i, _vp, _vp, _vp]),
     'sfm_build_tables': (_i, [_D, _vp, _vp, _vp, _vp, _vp]),
     'sfm_ingest_u8': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'sfm_eval_depth_scratch_bytes': (C.c_size_t, [_i, _i, _i]),
+    'sfm_eval_depth': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp]),
     'sfm_disp_activation': (_i, [C.c_longlong, _vp, _vp, _vp, _vp]),
     'sfm_pose_reduce': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'sfm_warp_forward': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

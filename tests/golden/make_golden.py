@@ -176,6 +176,38 @@ def make_edge_smooth():
     np.savez_compressed(os.path.join(HERE, 'edge_smooth.npz'), **blob)
 
 
+def make_eval():
+    """evaluate.py:94-103 restated line by line with the shim's F.resize_images / F.clip, followed by the reference's
+    own kitti_eval.depth_util.compute_depth_errors (pure numpy, imported unmodified)."""
+    import kitti_eval.depth_util as ref_du
+    F = chainer.functions
+    rs = np.random.RandomState(9)
+    B, h, w, Hg, Wg = 2, 32, 104, 94, 311
+    min_depth, max_depth = 1e-3, 80.0
+    gt = (rs.uniform(1.0, 60.0, (B, Hg // 8 + 2, Wg // 8 + 2)).repeat(8, 1).repeat(8, 2)[:, :Hg, :Wg]
+          * rs.uniform(0.9, 1.1, (B, Hg, Wg))).astype(np.float32)
+    pred_depth = (0.37 * gt[:, ::3, ::3][:, :h, :w] * rs.uniform(0.7, 1.4, (B, h, w))).astype(np.float32)[:, None]
+    pred_depth[0, 0, :2] = 1e-5            # below min_depth: clipped
+    pred_depth[1, 0, -2:] = 500.0          # above max_depth after scaling irrelevant: clipped before
+    mask = (rs.uniform(0, 1, (B, Hg, Wg)) < 0.4)
+    mask[:, :Hg // 3] = False              # KITTI crop: no ground truth in the sky
+    out = []
+    for even in (True, False):
+        mk = mask.copy()
+        if (int(mk.sum()) % 2 == 0) != even:
+            mk[tuple(np.argwhere(mk)[0])] = False
+        pd = F.resize_images(pred_depth, gt.shape[1:]).data                  # evaluate.py:94
+        pd = F.clip(pd, min_depth, max_depth).data[:, 0]                      # :95
+        pdm, gtm = pd[mk], gt[mk]                                             # :99-100
+        scale_factor = np.median(gtm) / np.median(pdm)                        # :101
+        pdm = pdm * scale_factor                                              # :102 (pred_depth *= scale_factor)
+        out.append((mk, ref_du.compute_depth_errors(gtm, pdm), scale_factor))
+        print('eval', 'even' if even else 'odd', int(mk.sum()), out[-1][1], scale_factor)
+    np.savez_compressed(os.path.join(HERE, 'eval_depth.npz'), pred_depth=pred_depth, gt=gt, min_depth=min_depth,
+                        max_depth=max_depth, mask_even=out[0][0], errors_even=out[0][1], scale_even=out[0][2],
+                        mask_odd=out[1][0], errors_odd=out[1][1], scale_odd=out[1][2])
+
+
 def make_ingest():
     """The data layer in front of the loss: the reference's own load_as_float_norm
     (datasets/kitti/kitti_raw_dataset.py:12-14) and _transform = data_augmentation + get_multi_scale_intrinsics
@@ -268,6 +300,9 @@ def main():
     if '--edge-only' in sys.argv:
         make_edge_smooth()
         return
+    if '--eval-only' in sys.argv:
+        make_eval()
+        return
     if '--ingest-only' in sys.argv:
         make_ingest()
         return
@@ -299,6 +334,7 @@ def main():
     make_seam()
     make_ingest()
     make_edge_smooth()
+    make_eval()
     print('golden fixtures written to', HERE)
 
 
