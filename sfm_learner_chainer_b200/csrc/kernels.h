@@ -26,6 +26,7 @@ struct SfmPrepParams {
   long long pix_begin[SFM_MAX_SCALES];
   int n_pyr_blocks;
   int vec0;          // scale 0 copied 4 pixels per thread
+  int band, split;   // full-resolution rows per pyramid CTA; warps sharing one row
 };
 
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);

@@ -2,13 +2,15 @@
 // NHWC4 so that every bilinear tap of the warp is one 16-byte load, the 3x4 projection tables
 // (proj_tgt_to_src, transform.py:64-91) and inverse intrinsics (F.batch_inv, transform.py:105), and the
 // reset of the fp64 reduction cells the fused loss kernel accumulates into.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace {
 
 constexpr int kPrepThreads = 256;
-constexpr int kBand = 8;          // full-resolution rows per pyramid CTA
+constexpr int kBandMax = 8;       // full-resolution rows per pyramid CTA (p.band = 8 / p.split)
 
 // Pyramid CTA = (image, band of kBand full-resolution rows).  It copies the band to scale 0 and produces
 // every coarser-scale row whose top tap row v0 lies in the band, so the full-resolution planes are read
@@ -20,6 +22,7 @@ constexpr int kBand = 8;          // full-resolution rows per pyramid CTA
 // y = ((w1*a + w2*b) + w3*c) + w4*d in fp32.  Scale 0 is the identity and is copied.
 // Source images carry the zero border of the padded layout (common.cuh): column w of every row and the
 // two rows below the image.
+template <int SPLIT>
 __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_constant__ SfmPrepParams p) {
   const int blk = blockIdx.x;
   cudaTriggerProgrammaticLaunchCompletion();      // the smoothness kernel may start once every CTA of this grid runs
@@ -60,6 +63,10 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
   }
 
   // ---- pyramid
+  // p.split warps share one row (x interleaved in units of 32 texels): small batches are latency-bound here -- a warp
+  // walks its scale-0 row and then its rows of the coarser scales one 32-texel iteration at a time -- so they get
+  // shorter walks (and p.band = 8 / p.split rows per CTA) instead of idle SMs
+  constexpr int kBand = kBandMax / SPLIT, split = SPLIT;
   const int n_bands = (p.H + kBand - 1) / kBand;
   const int img = blk / n_bands;            // [0, B): target b ; [B, B + B*S): source (b, i)
   const int band = blk - img * n_bands;
@@ -68,7 +75,10 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
   const int H = p.H, W = p.W;
   const size_t plane = (size_t)H * W;
   const float* __restrict__ base = is_src ? p.src + (size_t)(img - p.B) * 3 * plane : p.tgt + (size_t)img * 3 * plane;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) / split, sub = (threadIdx.x >> 5) % split, lane = threadIdx.x & 31;
+  constexpr int nrow = (kPrepThreads / 32) / split;       // rows walked concurrently by the CTA
+  constexpr int x_step = 32 * split;
+  const int x_first = lane + 32 * sub;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < p.ns; ++s) {
     const int h = H >> s, w = W >> s;
@@ -76,12 +86,12 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
     float4* __restrict__ out = is_src ? p.src_pyr[s] + (size_t)(img - p.B) * sfm_src_rows(h) * pitch
                                       : p.tgt_pyr[s] + (size_t)img * h * w;
     if (s == 0) {
-      for (int y = Y0 + warp; y < Y1; y += kPrepThreads / 32) {
+      for (int y = Y0 + warp; y < Y1; y += nrow) {
         const float* __restrict__ row = base + (size_t)y * W;
         float4* __restrict__ orow = out + (size_t)y * pitch;
-        for (int x = lane; x < W; x += 32)
+        for (int x = x_first; x < W; x += x_step)
           orow[x] = make_float4(__ldg(row + x), __ldg(row + plane + x), __ldg(row + 2 * plane + x), 0.f);
-        if (is_src && lane == 0) orow[W] = zero4;
+        if (is_src && lane == 0 && sub == 0) orow[W] = zero4;
       }
     } else {
       const double stepx = (w > 1) ? __ddiv_rn((double)(W - 1), (double)(w - 1)) : 0.0;
@@ -89,14 +99,14 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
       // candidate rows: those whose v0 can fall in [Y0, Y1); the exact test is below
       const int y_lo = (stepy > 0.0) ? max(0, (int)((double)Y0 / stepy) - 1) : 0;
       const int y_hi = (stepy > 0.0) ? min(h, (int)((double)Y1 / stepy) + 2) : h;
-      for (int y = y_lo + warp; y < y_hi; y += kPrepThreads / 32) {
+      for (int y = y_lo + warp; y < y_hi; y += nrow) {
         const double v = (y == h - 1 && h > 1) ? (double)(H - 1) : __dmul_rn((double)y, stepy);
         const int v0 = min(max((int)floor(v), 0), H - 2);
         if (v0 < Y0 || v0 >= Y1) continue;          // another band owns this row (warp-uniform)
         const double va = __dsub_rn((double)(v0 + 1), v), vb = __dsub_rn(v, (double)v0);
         const float* __restrict__ r0 = base + (size_t)v0 * W;
         float4* __restrict__ orow = out + (size_t)y * pitch;
-        for (int x = lane; x < w; x += 32) {
+        for (int x = x_first; x < w; x += x_step) {
           const double u = (x == w - 1 && w > 1) ? (double)(W - 1) : __dmul_rn((double)x, stepx);
           const int u0 = min(max((int)floor(u), 0), W - 2);
           const double ua = __dsub_rn((double)(u0 + 1), u), ub = __dsub_rn(u, (double)u0);
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
           }
           orow[x] = make_float4(r[0], r[1], r[2], 0.f);
         }
-        if (is_src && lane == 0) orow[w] = zero4;
+        if (is_src && lane == 0 && sub == 0) orow[w] = zero4;
       }
     }
     // the two zero rows below a source image belong to the last band
@@ -154,10 +164,22 @@ __global__ void sfm_pyramid_export_kernel(const float4* __restrict__ pyr, float*
 
 int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
   SfmPrepParams p = p_in;
+  // split the rows over 2 or 4 warps while the grid stays within one wave of 256-thread CTAs (4 per SM)
+  p.split = 1;
+  {
+    const char* e = getenv("SFM_PREP_SPLIT");     // development knob
+    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) p.split = atoi(e);
+    else
+      while (p.split < 4 && (long long)p.B * (1 + p.S) * ((p.H * 2 * p.split + kBandMax - 1) / kBandMax) <= 148 * 4) p.split *= 2;
+  }
+  p.band = kBandMax / p.split;
+  const int kBand = p.band;
   p.n_pyr_blocks = p.do_pyramid ? p.B * (1 + p.S) * ((p.H + kBand - 1) / kBand) : 0;
   const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;
   const int tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
-  sfm_prep_kernel<<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
+  if (p.split == 4) sfm_prep_kernel<4><<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
+  else if (p.split == 2) sfm_prep_kernel<2><<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
+  else sfm_prep_kernel<1><<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
   SFM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
