@@ -21,9 +21,14 @@ namespace {
 
 __device__ __forceinline__ float norm_u8(uint8_t p) { return __fsub_rn(__fdiv_rn((float)p, 127.5f), 1.f); }
 
+// 256-entry table of norm_u8 in shared memory: the IEEE division costs ~17 issue slots and every output pixel needs
+// twelve of them; the table holds exactly the values the division would produce.
 __global__ void __launch_bounds__(256) sfm_ingest_u8_kernel(const uint8_t* __restrict__ frames, const SfmAugment* __restrict__ aug,
                                                             float* __restrict__ tgt, float* __restrict__ src, int B, int S, int H,
                                                             int W) {
+  __shared__ float s_norm[256];
+  s_norm[threadIdx.x] = norm_u8((uint8_t)threadIdx.x);
+  __syncthreads();
   const int img = blockIdx.y;                 // b * (1 + S) + j ; j == 0 is the target frame
   const int b = img / (1 + S), j = img - b * (1 + S);
   SfmAugment a;
@@ -47,10 +52,15 @@ __global__ void __launch_bounds__(256) sfm_ingest_u8_kernel(const uint8_t* __res
     const float w3 = (float)__dmul_rn(vb, ua), w4 = (float)__dmul_rn(vb, ub);
     const uint8_t* __restrict__ t0 = in + ((size_t)v0 * W + u0) * 3;      // taps (v0,u0),(v0,u0+1): 6 contiguous bytes
     const uint8_t* __restrict__ t1 = t0 + (size_t)W * 3;
+    uint8_t q[12];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      q[k] = __ldg(t0 + k);
+      q[6 + k] = __ldg(t1 + k);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      out[c * plane + pix] = sfm_blend(w1, w2, w3, w4, norm_u8(__ldg(t0 + c)), norm_u8(__ldg(t0 + 3 + c)), norm_u8(__ldg(t1 + c)),
-                                       norm_u8(__ldg(t1 + 3 + c)));
+      out[c * plane + pix] = sfm_blend(w1, w2, w3, w4, s_norm[q[c]], s_norm[q[3 + c]], s_norm[q[6 + c]], s_norm[q[9 + c]]);
   }
 }
 
