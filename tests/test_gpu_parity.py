@@ -341,6 +341,27 @@ def test_host_submit_wait_with_two_contexts_in_flight():
     assert lib.sfm_loss_step_host_wait(None) == L.SFM_E_NULL_POINTER
 
 
+@pytest.mark.parametrize('flagset', ['v1_ssim', 'v1_odom'])
+def test_results_do_not_depend_on_the_task_height(flagset, monkeypatch):
+    """The launch policy picks the task height (rows / runs per warp task) from a cost model; any height must give
+    the same per-pixel gradients bit for bit (only the order of the fp64 cell sums changes) -- guards the halo and
+    segment-boundary logic for heights that are not powers of two."""
+    flags = FLAGSETS[flagset]
+    d = make_snippets(2, 2, 72, 136, seed=45, harsh=True)
+    g = dev_inputs(d)
+    op = _op(flags)
+    monkeypatch.delenv('SFM_HSEG', raising=False)
+    l0, g0 = op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    ref = (host(l0), [host(x) for x in g0['gdisps']], host(g0['gposes']))
+    for hseg in (4, 5, 8, 9, 11, 13, 17, 23, 37, 64):
+        monkeypatch.setenv('SFM_HSEG', str(hseg))
+        l1, g1 = op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+        np.testing.assert_allclose(host(l1), ref[0], rtol=1e-6, err_msg='hseg %d' % hseg)
+        assert_grad_close(host(g1['gposes']), ref[2], what='gposes, hseg %d (fp32 per-task accumulation order)' % hseg)
+        for s in range(4):
+            np.testing.assert_array_equal(host(g1['gdisps'][s]), ref[1][s], err_msg='hseg %d scale %d' % (hseg, s))
+
+
 def test_torch_autograd_bridge_and_model_surface():
     """SFMLearner.__call__ surface (base_model.py:48-124) with stub nets: loss, five reports, gradients
     reaching the producers of pred_disps / pred_poses / pred_maskes."""
