@@ -315,7 +315,7 @@ class Workload(object):
         return float(np.mean(ts)), float(ts[len(ts) // 2])
 
 
-def run_e2e(cfg_name, steps, device, n_ctx=2, u8=False):
+def run_e2e(cfg_name, steps, device, n_ctx=3, u8=False):
     """Same metric through the host-buffer C-ABI entry point: pinned host inputs -> H2D -> pyramid + fused
     fwd+bwd -> D2H of the five losses and every gradient, EVERY step.  `n_ctx` host contexts are used alternately
     (sfm_loss_step_host_submit / _wait), the way a data loader keeps the next step's copies in flight while the
@@ -520,11 +520,11 @@ def run_b200(args):
     if world == 1:
         # ---- e2e through the host-buffer C-ABI entry point
         e2e_steps = max(5, min(200, args.steps))
-        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device, n_ctx=2)
+        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device, n_ctx=3)
         ev1, _, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=1)
-        ev8, h2d8, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=2, u8=True)
+        ev8, h2d8, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=3, u8=True)
         line['e2e'] = dict(value=ev, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
-                           api='sfm_loss_step_host_submit/_wait, two host contexts used alternately (pinned host buffers; every step: '
+                           api='sfm_loss_step_host_submit/_wait, three host contexts used in rotation (pinned host buffers; every step: '
                                'H2D of all inputs, pyramid + fused fwd+bwd, D2H of losses and all gradients)',
                            synchronous_value=ev1, synchronous_api='sfm_loss_step_host (one step at a time)',
                            u8_frames_value=ev8, u8_frames_h2d_bytes_per_step=h2d8,
