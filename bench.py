@@ -423,7 +423,7 @@ def run_b200(args):
     # steps can overwrite their rows) into one asynchronous call, the way a trainer that reports every few
     # iterations would.  At ~48 us per step the per-step call is host-bound (measured at N=2: 52.0 vs 47.1 us).
     pending = []
-    every = args.allreduce_every if args.allreduce_every > 0 else wl.nsets
+    every = args.allreduce_every if args.allreduce_every > 0 else max(1, min(wl.nsets, args.steps))   # >= 1 call inside the timed region
     staging = [torch.zeros_like(wl.all_losses) for _ in range(2)]
     flip = [0]
 
