@@ -63,15 +63,23 @@ struct IC { static constexpr int value = N; };
 #ifndef SFM_MINB_SSIM
 #define SFM_MINB_SSIM 12
 #endif
-template <bool GRAD, bool ACCUM, bool DEBUG, bool RAW>
-__global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
-  __shared__ float4 sP[3];
+// NW = warps per CTA.  NW == 1: one warp walks the strip segment once per source.  NW == 2 (two sources, small
+// batches): the two warps of a CTA walk the same segment at the same time, one source each, so a task is half as
+// long and -- for the same number of resident warps -- twice as tall (half the halo rows).  gdisp stays
+// deterministic: warp 1 hands its per-row term to warp 0 through shared memory (one CTA barrier per row) and warp 0
+// applies both in the order of the sequential loop, with the same fused multiply-adds.
+template <bool GRAD, bool ACCUM, bool DEBUG, bool RAW, int NW>
+__global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
+  __shared__ float4 sP_all[NW][3];
+  __shared__ float sG[(NW > 1) ? 3 * 2 * 32 : 1];       // [ring slot][gdd | dsc][lane] of warp 1's row term
+  const int wi = (NW > 1) ? (int)(threadIdx.x >> 5) : 0;
+  float4* const sP = sP_all[wi];
   // two-row delay line of forward records: [slot][field][lane], written in stage A of row r and read back by
   // the same lane in stages E/F two steps later (no synchronisation needed).  In registers these 51 values
   // pushed the kernel over its 168-register budget (17-27 local-memory spills per three rows).
-  __shared__ float sRec[(GRAD && SFM_SSIM_SREC) ? 3 * 18 * 32 : 1];
-  const int lane = threadIdx.x;
-  float* const myrec = sRec + lane;
+  __shared__ float sRec[(GRAD && SFM_SSIM_SREC) ? NW * 3 * 18 * 32 : 1];
+  const int lane = threadIdx.x & 31;
+  float* const myrec = sRec + wi * (3 * 18 * 32) + lane;
   const StripTask t = decode_strip(p, blockIdx.x);
   const int s = t.s, b = t.b, h = p.h[s], w = p.w[s], S = p.S;
   const Geo geo = make_geo(p, s);
@@ -104,13 +112,14 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
   const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end) are warped
   const bool opaque_true = p.hseg != 0x7fffffff;       // always true, unknown to ptxas: basic-block fence (see step)
 
-  for (int i = 0; i < S; ++i) {
+  for (int i = (NW > 1) ? wi : 0; i < ((NW > 1) ? wi + 1 : S); ++i) {
     __syncwarp();
     if (lane < 12) reinterpret_cast<float*>(sP)[lane] = __ldg(p.proj + (((size_t)b * S + i) * p.ns + s) * 12 + lane);
     __syncwarp();
     const float P3 = sP[0].w, P7 = sP[1].w, P11 = sP[2].w;
     float accA[3] = {0.f, 0.f, 0.f}, accB[3] = {0.f, 0.f, 0.f}, accC[3] = {0.f, 0.f, 0.f};
     const bool first = (i == 0);
+    const bool writer = (NW == 1) || (wi == 0);          // the warp that loads / stores gdisp
     const float4* __restrict__ img = p.src_pyr[s] + ((size_t)b * S + i) * src_img;
     // rings: window row sums (P, P^2, P.T, T, T^2 per channel), gradient-field row sums, forward records
     float hs[3][15], gs[3][9];
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
       I10 = __ldg(tp + geo.pitch);
       I11 = __ldg(tp + geo.pitch + 1);
       load_dT(r + 1, dq[nx], Tq[nx]);
-      if (GRAD && (ACCUM || !first)) {
+      if (GRAD && (ACCUM || !first) && writer) {
         const int rf = r - 2;
         g_old = (col_own && rf >= t.y0 && rf < t.y1) ? gdisp[rf * w + xx] : 0.f;
       }
@@ -368,8 +377,15 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
         accB[0] = fmaf(e0, yfb, accB[0]); accB[1] = fmaf(e1, yfb, accB[1]); accB[2] = fmaf(e2, yfb, accB[2]);
         accC[0] += gq0; accC[1] += gq1; accC[2] += gq2;
         float* gp = gdisp + rf * w + xx;
-        const float gval = g_prev - gdd * rb.dsc;
-        if (do_f) *gp = gval;
+        float gval = g_prev - gdd * rb.dsc;
+        if (NW > 1) {
+          // warp 1 -> warp 0: (gdd, dsc) of the second source for this row; warp 0 continues the sequential chain
+          float* slot = sG + cur * 64 + lane;
+          if (wi == 1) { slot[0] = gdd; slot[32] = rb.dsc; }
+          __syncthreads();
+          if (wi == 0) gval = gval - slot[0] * slot[32];
+        }
+        if (do_f && writer) *gp = gval;
       }
 #if SFM_SSIM_FENCE
       }
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
       step(IC<2>{}, r + 2);
     }
     // ---- flush: expand (A, B, C) to dL/dP = sum gq (x) (X, Y, Z, 1) with X = depth*((k0 x + k2) + k1 y) ...
-    const bool last = (i == S - 1);
+    const bool last = (NW > 1) || (i == S - 1);
     if (GRAD || last) {
       float acc[12];
       if (GRAD) {
@@ -409,10 +425,10 @@ __global__ void __launch_bounds__(32, SFM_MINB_SSIM) sfm_ssim_march_kernel(const
 }  // namespace
 
 template <typename K>
-static int launch_ssim_kernel(K kernel, const SfmFusedParams& p, cudaStream_t stream) {
+static int launch_ssim_kernel(K kernel, const SfmFusedParams& p, cudaStream_t stream, int nw = 1) {
   const int n_tasks = p.task_begin[SFM_MAX_SCALES];
   if (sfm_ev_start) SFM_CUDA_CHECK(cudaEventRecord(sfm_ev_start, stream));
-  SFM_CUDA_CHECK(sfm_launch_kernel(kernel, n_tasks, 32, stream, !sfm_ev_start, p));
+  SFM_CUDA_CHECK(sfm_launch_kernel(kernel, n_tasks, 32 * nw, stream, !sfm_ev_start, p));
   if (sfm_ev_stop) SFM_CUDA_CHECK(cudaEventRecord(sfm_ev_stop, stream));
   return 0;
 }
@@ -426,28 +442,36 @@ static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug,
   // waves x rows; below one wave the busiest scheduler holds w = ceil(tasks / schedulers) warps and runs them at
   // a relative issue efficiency of 0.66 / 0.9 / 1.0 for w = 1 / 2 / 3 (a lone warp cannot hide its own latencies).
   // Example cfg2 (B=4, 128x416): hseg 8 -> 1296 tasks, w=3, 12 rows: 36.8 us; hseg 11 -> 976 tasks, w=2, 15 rows: 33.4 us.
+  // With two sources and a sub-wave grid the sources can also be split over the two warps of a CTA (NW = 2): a task
+  // is then one pass long and there are twice as many warps, so the same occupancy is reached with taller segments
+  // (fewer halo rows); the per-row CTA barrier is charged 5 %.
   (void)want_warps;
-  int hseg = 64;
+  int hseg = 64, nw = 1;
   {
     const long long sched = (long long)g_num_sms * 4, slots = (long long)g_num_sms * SFM_MINB_SSIM;
+    const bool may_split = grad && !debug && p.raw_disp_mask == 0 && p.S == 2 && !getenv("SFM_SSIM_NOSPLIT");
     double best = 1e300;
-    for (int h = 8; h <= 64; ++h) {
-      long long n = 0;
-      for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + h - 1) / h);
-      const double rows = 3.0 * ((h + 4 + 2) / 3);
-      double cost;
-      if (n > slots) {
-        cost = rows * 3.0 * (double)((n + slots - 1) / slots);
-      } else {
-        const long long w = (n + sched - 1) / sched;
-        cost = rows * (double)w / (w <= 1 ? 0.66 : w == 2 ? 0.9 : 1.0);
+    for (int cand = 1; cand <= (may_split ? 2 : 1); ++cand)
+      for (int h = 8; h <= 64; ++h) {
+        long long n = 0;
+        for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + h - 1) / h);
+        const long long warps = n * cand;
+        const double rows = 3.0 * ((h + 4 + 2) / 3) * (cand == 1 ? p.S : 1) * (cand == 1 ? 1.0 : 1.05);
+        double cost;
+        if (warps > slots) {
+          cost = rows * 3.0 * (double)((warps + slots - 1) / slots);
+        } else {
+          const long long w = (warps + sched - 1) / sched;
+          cost = rows * (double)w / (w <= 1 ? 0.66 : w == 2 ? 0.9 : 1.0);
+        }
+        if (cost < best || (cost == best && cand == nw)) { best = cost; hseg = h; nw = cand; }
       }
-      if (cost <= best) { best = cost; hseg = h; }
-    }
   }
   {
-    const char* e = getenv("SFM_HSEG");          // development knob
+    const char* e = getenv("SFM_HSEG");          // development knobs
     if (e && atoi(e) > 0) hseg = atoi(e);
+    const char* f = getenv("SFM_SSIM_NW");
+    if (f && (atoi(f) == 1 || (atoi(f) == 2 && grad && !debug && p.raw_disp_mask == 0 && p.S == 2))) nw = atoi(f);
   }
   p.hseg = hseg;
   int total = 0;
@@ -464,11 +488,17 @@ static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug,
   p.task_begin[SFM_MAX_SCALES] = total;
   int rc;
   const bool raw = p.raw_disp_mask != 0;
+  if (nw == 2) {
+    rc = accum ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false, false, 2>, p, stream, 2)
+               : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false, false, 2>, p, stream, 2);
+    if (rc) return rc;
+    return launch_epilogue(p, stream);
+  }
 #define SFM_SSIM(GR, AC)                                                                                   \
-  rc = raw ? (debug ? launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, true, true>, p, stream)             \
-                    : launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, false, true>, p, stream))           \
-           : (debug ? launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, true, false>, p, stream)            \
-                    : launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, false, false>, p, stream))
+  rc = raw ? (debug ? launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, true, true, 1>, p, stream)             \
+                    : launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, false, true, 1>, p, stream))           \
+           : (debug ? launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, true, false, 1>, p, stream)            \
+                    : launch_ssim_kernel(sfm_ssim_march_kernel<GR, AC, false, false, 1>, p, stream))
   if (grad) {
     if (accum) { SFM_SSIM(true, true); } else { SFM_SSIM(true, false); }
   } else {

@@ -234,7 +234,8 @@ def test_shard_sum_equals_full_batch_at_full_size(cfg):
             [x[sl].contiguous() for x in g['disps']], g['poses'][sl].contiguous(),
             [x[sl].contiguous() for x in g['logits']])
         acc += host(ls).astype(np.float64)
-        np.testing.assert_allclose(host(gs['gposes']), host(gf['gposes'])[sl], rtol=1e-5, atol=1e-8)
+        # the shard may run with another task shape (launch policy), i.e. another fp32 accumulation order per task
+        assert_grad_close(host(gs['gposes']), host(gf['gposes'])[sl], what='gposes of shard %d' % lo)
         np.testing.assert_array_equal(host(gs['gdisps'][0]), host(gf['gdisps'][0])[sl])
     np.testing.assert_allclose(acc, host(lf), rtol=2e-6)
 
@@ -360,6 +361,36 @@ def test_results_do_not_depend_on_the_task_height(flagset, monkeypatch):
         assert_grad_close(host(g1['gposes']), ref[2], what='gposes, hseg %d (fp32 per-task accumulation order)' % hseg)
         for s in range(4):
             np.testing.assert_array_equal(host(g1['gdisps'][s]), ref[1][s], err_msg='hseg %d scale %d' % (hseg, s))
+
+
+def test_source_split_ssim_kernel_equals_sequential_kernel(monkeypatch):
+    """Small two-source batches run the SSIM kernel with the sources split over the two warps of a CTA (NW = 2);
+    the per-pixel gradients must equal the one-warp-per-task kernel bit for bit (same fused multiply-adds in the
+    same order), losses and pose gradients to rounding of the partial sums."""
+    flags = FLAGSETS['v1_ssim']
+    for (B, H, W, seed) in ((4, 128, 416, 46), (2, 72, 136, 47)):
+        d = make_snippets(B, 2, H, W, seed=seed, harsh=bool(seed & 1))
+        g = dev_inputs(d)
+        res = []
+        for nw in ('1', '2'):
+            monkeypatch.setenv('SFM_SSIM_NW', nw)
+            l, gr = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+            res.append((host(l), [host(x) for x in gr['gdisps']], host(gr['gposes'])))
+        monkeypatch.delenv('SFM_SSIM_NW')
+        np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-6)
+        assert_grad_close(res[1][2], res[0][2], what='gposes')
+        for s in range(4):
+            np.testing.assert_array_equal(res[1][1][s], res[0][1][s], err_msg='gdisp scale %d' % s)
+        # and without the smoothness term (the kernel then writes gdisp without reading it)
+        flags0 = dict(flags, smooth_reg=0.0)
+        out = []
+        for nw in ('1', '2'):
+            monkeypatch.setenv('SFM_SSIM_NW', nw)
+            l, gr = _op(flags0).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+            out.append([host(x) for x in gr['gdisps']])
+        monkeypatch.delenv('SFM_SSIM_NW')
+        for s in range(4):
+            np.testing.assert_array_equal(out[1][s], out[0][s], err_msg='gdisp scale %d (no smoothness)' % s)
 
 
 def test_torch_autograd_bridge_and_model_surface():
