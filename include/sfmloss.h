@@ -43,7 +43,7 @@ extern "C" {
 #define SFM_FLAG_TABLES_PROVIDED 0x1u /* caller supplies proj/kinv tables (bit-exact tests; the reference
                                          itself builds P on the host, transform.py:76-90) */
 #define SFM_FLAG_REUSE_PYRAMID 0x2u   /* workspace already holds this batch's image pyramid */
-#define SFM_FLAG_NO_TMA 0x4u          /* force the plain-load tile path (debug / A-B measurement) */
+#define SFM_FLAG_NO_TMA 0x4u          /* reserved (accepted and ignored: the marching kernels stage nothing through TMA) */
 #define SFM_FLAG_EDGE_AWARE_SMOOTH 0x8u /* the smoothness term is compute_disp_smooth(curr_tgt_img, pred_disps[ns])
                                          (base_model.py:144-155), the edge-aware alternative the reference keeps
                                          commented out at its call site (:78-80), instead of compute_smooth_loss */
