@@ -214,6 +214,27 @@ def test_identity_pose_and_all_out_of_view():
     assert not host(grads['gposes']).any()
 
 
+def test_pure_x_translation_is_an_analytic_shift():
+    """T4 property on the device: constant depth + pure x translation = constant sub-pixel shift of the source."""
+    from sfm_learner_chainer_b200 import projective_inverse_warp
+    from tests.test_oracle_golden import _x_translation_case
+    img, K, pose, depth, shift = _x_translation_case(np.float32)
+    out, u0, v0, inb = projective_inverse_warp(to_dev(img), to_dev(depth), to_dev(pose), to_dev(K), return_indices=True)
+    P = host(out)
+    H, W = img.shape[2:]
+    k = int(np.floor(shift))
+    f = np.float32(shift - k)
+    x = np.arange(W)
+    inside = (x + shift > 0.01) & (x + shift < W - 1.01)
+    xi = x[inside]
+    ref = (1 - f) * img[..., xi + k] + f * img[..., xi + k + 1]
+    # rows 0 and H-1 sit exactly on yn = -1 / +1: out of view by the strict rule (transform.py:128-131)
+    np.testing.assert_allclose(P[:, :, 1:-1][..., inside], ref[:, :, 1:-1], rtol=0, atol=2e-5)   # fp32 coordinates: f is known to ~1e-5
+    np.testing.assert_array_equal(host(u0)[0][1:-1][:, inside], np.broadcast_to(xi + k, (H - 2, xi.size)))
+    np.testing.assert_array_equal(host(inb)[0][1:-1][:, inside], 1)
+    assert np.all(P[:, :, 0] == 0) and np.all(P[:, :, -1] == 0)
+
+
 @pytest.mark.parametrize('cfg', ['cfg4', 'cfg2'])
 def test_shard_sum_equals_full_batch_at_full_size(cfg):
     """Size-independent property at BASELINE.json's shapes: snippet shards (B_global = full batch) sum to

@@ -116,3 +116,29 @@ def test_identity_pose_reproduces_source():
     inb = (rec['grid']['inx'] & rec['grid']['iny']).reshape(32, 104)
     assert inb[1:-1, 1:-1].all()
     np.testing.assert_allclose(P[0][:, inb], d['src'][0, 0][:, inb], atol=2e-4)
+
+
+def _x_translation_case(dt=np.float64, H=24, W=40, tx=0.0123, depth=2.5, fx=30.0):
+    rs = np.random.RandomState(5)
+    img = rs.uniform(-1, 1, (1, 3, H, W)).astype(dt)
+    K = np.array([[[fx, 0, (W - 1) / 2.0], [0, fx, (H - 1) / 2.0], [0, 0, 1]]], dt)
+    pose = np.array([[0, 0, 0, tx, 0, 0]], dt)
+    return img, K, pose, np.full((1, H * W), depth, dt), fx * tx / depth
+
+
+def test_pure_x_translation_is_an_analytic_shift():
+    """Constant depth d and a pure x translation t: u = x + fx*t/d for every pixel, so the warp is the source
+    shifted by a constant sub-pixel amount."""
+    img, K, pose, depth, shift = _x_translation_case()
+    P, rec = O.projective_inverse_warp(img, depth, pose, K)
+    H, W = img.shape[2:]
+    k = int(np.floor(shift))
+    f = shift - k
+    x = np.arange(W)
+    inside = (x + shift > 0) & (x + shift < W - 1)            # strictly inside (-1, 1) after normalisation
+    ref = np.zeros_like(img)
+    xi = x[inside]
+    ref[..., xi] = (1 - f) * img[..., xi + k] + f * img[..., np.minimum(xi + k + 1, W - 1)]
+    # rows 0 and H-1 sit exactly on yn = -1 / +1: not strictly inside, hence out of view (transform.py:128-131)
+    np.testing.assert_allclose(P[:, :, 1:-1][..., inside], ref[:, :, 1:-1][..., inside], rtol=0, atol=1e-8)   # z = q2 + 1e-10 (transform.py:123)
+    assert np.all(P[..., ~inside] == 0) and np.all(P[:, :, 0] == 0) and np.all(P[:, :, -1] == 0)
