@@ -1,0 +1,60 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`):
+SURVEY T6 -- the G-GPU snippet-sharded result equals the 1-GPU result.  One process per GPU over NCCL, each rank runs
+ShardedViewSynthesisLoss on its block of snippets with B_global; its gradients must be final (no communication) and
+the all-reduced loss partials must equal the full-batch losses."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLAGS = dict(smooth_reg=0.1, exp_reg=0.0, ssim_rate=0.15)
+
+
+def _worker(rank, world, port, out_dir, B):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from sfm_learner_chainer_b200.distributed import ShardedViewSynthesisLoss, shard_arrays, shard_range
+    from sfm_learner_chainer_b200.synthetic import make_snippets
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    d = make_snippets(B, 2, 128, 416, seed=90)
+    mine = shard_arrays(dict(tgt=d['tgt'], src=d['src'], intrinsics=d['intrinsics'], disps=d['disps'], poses=d['poses'],
+                             logits=d['logits']), B, rank, world)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    op = ShardedViewSynthesisLoss(B_global=B, **FLAGS)
+    losses, grads, work = op.forward_backward(dev(mine['tgt']), dev(mine['src']), dev(mine['intrinsics']),
+                                              [dev(x) for x in mine['disps']], dev(mine['poses']), None, async_op=True)
+    work.wait()
+    torch.cuda.synchronize()
+    lo, hi = shard_range(B, rank, world)
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), losses=losses.cpu().numpy(), gposes=grads['gposes'].cpu().numpy(),
+             gdisp0=grads['gdisps'][0].cpu().numpy(), lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+def test_sharded_result_equals_single_gpu_result(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    import torch.multiprocessing as mp
+    from sfm_learner_chainer_b200 import ViewSynthesisLoss
+    from sfm_learner_chainer_b200.synthetic import make_snippets
+    from tests.gpu_util import dev_inputs, host, assert_grad_close
+    world, B = 2, 6
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), B), nprocs=world, join=True)
+    d = make_snippets(B, 2, 128, 416, seed=90)
+    g = dev_inputs(d)
+    lf, gf = ViewSynthesisLoss(**FLAGS).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], None)
+    for r in range(world):
+        z = np.load(tmp_path / ('rank%d.npz' % r))
+        sl = slice(int(z['lo']), int(z['hi']))
+        np.testing.assert_allclose(z['losses'][:5], host(lf)[:5], rtol=2e-6)            # every rank holds the full-batch losses
+        np.testing.assert_array_equal(z['gdisp0'], host(gf['gdisps'][0])[sl])            # shard gradients are final, bit for bit
+        assert_grad_close(z['gposes'], host(gf['gposes'])[sl], what='gposes of rank %d' % r)
