@@ -414,6 +414,37 @@ def test_source_split_ssim_kernel_equals_sequential_kernel(monkeypatch):
             np.testing.assert_array_equal(out[1][s], out[0][s], err_msg='gdisp scale %d (no smoothness)' % s)
 
 
+def test_chainer_function_node_adapter_with_a_duck_typed_base():
+    """the FunctionNode adapter (chainer_adapter.py) on a minimal stand-in for
+    chainer.function_node.FunctionNode -- apply() -> forward(inputs) -> one output; backward(indexes, grad_outputs)
+    returns the gradients of the requested inputs -- with torch CUDA tensors as the device arrays."""
+    import torch
+    from sfm_learner_chainer_b200.chainer_adapter import make_function_node_class
+
+    class FakeFunctionNode(object):                      # the two methods of the FunctionNode protocol the adapter relies on
+        def apply(self, inputs):
+            self.inputs = tuple(inputs)
+            return self.forward(self.inputs)
+
+    d = make_snippets(2, 2, 32, 104, seed=35)
+    flags = FLAGSETS['v1_odom']
+    L, G, _ = _oracle(d, flags)
+    g = dev_inputs(d)
+    Node = make_function_node_class(FakeFunctionNode)
+    fn = Node(_op(flags), g['tgt'], g['src'], g['intrinsics'])
+    loss, = fn.apply(tuple(g['disps']) + (g['poses'],) + tuple(g['logits']))
+    assert tuple(loss.shape) == ()
+    np.testing.assert_allclose(float(loss), L['total_loss'], rtol=1e-5)
+    np.testing.assert_allclose(host(fn.losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)     # the five chainer.report values
+    gy = torch.full((), 2.0, device='cuda')
+    want = (0, 4, 6)                                     # pred_disps[0], pred_poses, pred_maskes[1]
+    got = fn.backward(want, (gy,))
+    assert len(got) == 3
+    assert_grad_close(host(got[0]), 2.0 * G['gdisp'][0], what='gdisp[0]')
+    assert_grad_close(host(got[1]), 2.0 * G['gpose'], what='gpose')
+    assert_grad_close(host(got[2]), 2.0 * G['glogits'][1], what='glogits[1]')
+
+
 def test_torch_autograd_bridge_and_model_surface():
     """SFMLearner.__call__ surface (base_model.py:48-124) with stub nets: loss, five reports, gradients
     reaching the producers of pred_disps / pred_poses / pred_maskes."""
