@@ -1,6 +1,9 @@
+"""End-to-end (host-buffer) throughput of the loss path at cfg2 against the number of host contexts kept in flight,
+for float images and for uint8 frames (bench.py's run_e2e)."""
 import sys, os
-sys.path.insert(0, '/root/repo')
-os.chdir('/root/repo')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.chdir(ROOT)
 import torch, bench
 dev = torch.device('cuda', 0); torch.cuda.set_device(0)
 for n in (1, 2, 3, 4):
