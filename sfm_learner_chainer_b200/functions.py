@@ -147,9 +147,23 @@ class ViewSynthesisLoss(object):
                                             self._workspace(desc, tgt), C.c_void_p(D.current_stream(tgt))))
         return out
 
-    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, proj=None, kinv=None):
-        """Single fused pass: -> (losses (5,), dict(gdisps, gposes, glogits)) for upstream gradient 1."""
+    def build_pyramid(self, tgt, src):
+        """F.resize_images pyramid of this batch (base_model.py:70-72) into the operator's workspace.  It depends
+        on the input images alone, so a trainer can issue it for the next batch on a side stream while the CNNs
+        run; the following forward_backward(..., reuse_pyramid=True) then only builds the projection tables."""
+        B, S, _, H, W = src.shape
+        D.check_array(tgt, 'tgt_img', (B, 3, H, W))
+        D.check_array(src, 'src_imgs', (B, S, 3, H, W))
+        desc = self._desc(B, S, H, W)
+        L.check(self._lib.sfm_pyramid(C.byref(desc), _vp(tgt), _vp(src), self._workspace(desc, tgt),
+                                      C.c_void_p(D.current_stream(tgt))))
+
+    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, proj=None, kinv=None, reuse_pyramid=False):
+        """Single fused pass: -> (losses (5,), dict(gdisps, gposes, glogits)) for upstream gradient 1.
+        reuse_pyramid: the workspace already holds this batch's pyramid (build_pyramid)."""
         desc, inp = self._pack(tgt, src, intrinsics, disps, poses, logits, proj, kinv)
+        if reuse_pyramid:
+            desc.flags |= L.SFM_FLAG_REUSE_PYRAMID
         g, out = self._alloc_grads(desc, tgt)
         losses = D.empty(tgt, (5,))
         L.check(self._lib.sfm_loss_forward_backward(C.byref(desc), C.byref(inp), _vp(losses), C.byref(g),

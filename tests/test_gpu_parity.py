@@ -445,6 +445,24 @@ def test_chainer_function_node_adapter_with_a_duck_typed_base():
     assert_grad_close(host(got[2]), 2.0 * G['glogits'][1], what='glogits[1]')
 
 
+@pytest.mark.parametrize('flagset', ['v1_ssim', 'v1_odom'])
+def test_reuse_pyramid_flag(flagset):
+    """sfm_pyramid + SFM_FLAG_REUSE_PYRAMID (pyramid built ahead, e.g. for the next batch on a side stream) gives the
+    same result as the all-in-one call, bit for bit."""
+    flags = FLAGSETS[flagset]
+    d = make_snippets(2, 2, 64, 208, seed=36)
+    g = dev_inputs(d)
+    args = (g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    l0, g0 = _op(flags).forward_backward(*args)
+    op = _op(flags)
+    op.build_pyramid(g['tgt'], g['src'])
+    l1, g1 = op.forward_backward(*args, reuse_pyramid=True)
+    np.testing.assert_array_equal(host(l1), host(l0))
+    np.testing.assert_array_equal(host(g1['gposes']), host(g0['gposes']))
+    for s in range(4):
+        np.testing.assert_array_equal(host(g1['gdisps'][s]), host(g0['gdisps'][s]))
+
+
 def test_torch_autograd_bridge_and_model_surface():
     """SFMLearner.__call__ surface (base_model.py:48-124) with stub nets: loss, five reports, gradients
     reaching the producers of pred_disps / pred_poses / pred_maskes."""
