@@ -463,6 +463,34 @@ def test_reuse_pyramid_flag(flagset):
         np.testing.assert_array_equal(host(g1['gdisps'][s]), host(g0['gdisps'][s]))
 
 
+@pytest.mark.parametrize('flagset', ['v1', 'v1_ssim', 'v1_odom'])
+@pytest.mark.parametrize('B,S,H,W', [(1, 1, 32, 32),      # one source view, smallest legal size (4x4 at the coarsest scale)
+                                     (3, 3, 36, 60),      # odd source count, sizes that are not multiples of 8 (4x7 at scale 3)
+                                     (1, 5, 32, 40),      # five sources: three passes of the two-source kernel
+                                     (2, 2, 33, 57)])     # odd sizes: H >> s and W >> s truncate
+def test_edge_shapes_match_oracle(flagset, B, S, H, W):
+    flags = FLAGSETS[flagset]
+    d = make_snippets(B, S, H, W, seed=48, harsh=True)
+    L, G, _ = _oracle(d, flags)
+    g = dev_inputs(d)
+    losses, grads = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    np.testing.assert_allclose(host(losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)
+    assert_grad_close(host(grads['gposes']), G['gpose'], what='gposes')
+    for s in range(4):
+        assert_grad_close(host(grads['gdisps'][s]), G['gdisp'][s], what='gdisp[%d]' % s)
+        if flags['exp_reg']:
+            assert_grad_close(host(grads['glogits'][s]), G['glogits'][s], what='glogits[%d]' % s)
+
+
+def test_shapes_below_the_minimum_are_rejected():
+    from sfm_learner_chainer_b200 import lib as L
+    d = make_snippets(1, 2, 24, 40, seed=49)                  # 3x5 at the coarsest scale: below 4x4
+    g = dev_inputs(d)
+    with pytest.raises(L.SfmError) as e:
+        _op(FLAGSETS['v1']).forward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    assert e.value.code == L.SFM_E_INVALID_SHAPE or e.value.code == L.SFM_E_INVALID_DESC
+
+
 def test_torch_autograd_bridge_and_model_surface():
     """SFMLearner.__call__ surface (base_model.py:48-124) with stub nets: loss, five reports, gradients
     reaching the producers of pred_disps / pred_poses / pred_maskes."""
