@@ -52,7 +52,8 @@ extern "C" {
  * Problem descriptor.  Mirrors the reference's model flags (base_model.py:37-39:
  * smooth_reg, exp_reg, ssim_rate; experiments/sfm_learner_v1*.yml `architecture:` blocks) and the
  * tensor shapes SFMLearner.__call__ receives (base_model.py:48-58).
- * A flag <= 0 disables its term exactly like the Python truthiness tests at base_model.py:75,86,103,112;
+ * A flag equal to 0 disables its term (any non-zero value, negative included, enables it) exactly like the
+ * Python truthiness tests at base_model.py:75,86,103,112;
  * the explainability branch and SSIM are mutually exclusive as in the reference (:103-115).
  */
 typedef struct SfmDesc {
@@ -86,7 +87,7 @@ typedef struct SfmDesc {
  *                                   bit s of desc->raw_disp_scales is set)
  *   poses      (B,S,6)              models/pose_net.py:52-54 (rx,ry,rz,tx,ty,tz per source); (B,6*S,n) raw
  *                                   `poseout` map when desc->raw_pose_hw = n > 0
- *   logits[s]  (B,S,H>>s,W>>s)      models/pose_net.py:56-67; may be NULL when exp_reg <= 0
+ *   logits[s]  (B,S,H>>s,W>>s)      models/pose_net.py:56-67; may be NULL when exp_reg == 0
  *   proj       (B,S,n_scales,3,4)   only with SFM_FLAG_TABLES_PROVIDED: K4.T rows 0..2 (transform.py:86-88)
  *   kinv       (B,n_scales,3,3)     only with SFM_FLAG_TABLES_PROVIDED: inverse intrinsics (transform.py:105)
  */
@@ -102,7 +103,7 @@ typedef struct SfmInputs {
 } SfmInputs;
 
 /* Gradients w.r.t. the network outputs (base_model.py:59-63 are the producers).  Same shapes as the
- * corresponding inputs.  glogits may be NULL when exp_reg <= 0. */
+ * corresponding inputs.  glogits may be NULL when exp_reg == 0. */
 typedef struct SfmGrads {
   float* gdisps[SFM_MAX_SCALES];
   float* gposes;

@@ -27,6 +27,7 @@ struct SfmPrepParams {
   int n_pyr_blocks;
   int vec0;          // scale 0 copied 4 pixels per thread
   int band, split;   // full-resolution rows per pyramid CTA; warps sharing one row
+  int interleave;    // 1: CTAs ordered snippet by snippet (target, then its sources) instead of all targets first
 };
 
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
@@ -51,6 +52,8 @@ struct SfmFusedParams {
   int hseg;
   int nstrip[SFM_MAX_SCALES], nseg[SFM_MAX_SCALES];
   int task_begin[SFM_MAX_SCALES + 1];
+  int task_rev;      // 1: tasks are walked from the last to the first (the pyramid of the last snippets is the warmest in L2)
+  int pf_tasks;      // > 0: every L1 task prefetches (to L2) the source texels of the task pf_tasks ahead
   float wm1f[SFM_MAX_SCALES], hm1f[SFM_MAX_SCALES];   // (float)(w-1), (float)(h-1)
   float hwf[SFM_MAX_SCALES], hhf[SFM_MAX_SCALES];     // (w-1)/2, (h-1)/2
   const float4* tgt_pyr[SFM_MAX_SCALES];

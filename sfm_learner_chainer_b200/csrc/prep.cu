@@ -68,8 +68,12 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
   // shorter walks (and p.band = 8 / p.split rows per CTA) instead of idle SMs
   constexpr int kBand = kBandMax / SPLIT, split = SPLIT;
   const int n_bands = (p.H + kBand - 1) / kBand;
-  const int img = blk / n_bands;            // [0, B): target b ; [B, B + B*S): source (b, i)
+  int img = blk / n_bands;                  // [0, B): target b ; [B, B + B*S): source (b, i)
   const int band = blk - img * n_bands;
+  if (p.interleave) {                       // snippet-major order: (target b, sources (b, 0..S-1)), b ascending
+    const int b = img / (1 + p.S), j = img - b * (1 + p.S);
+    img = (j == 0) ? b : p.B + b * p.S + (j - 1);
+  }
   const int Y0 = band * kBand, Y1 = min(Y0 + kBand, p.H);
   const bool is_src = img >= p.B;
   const int H = p.H, W = p.W;
@@ -171,6 +175,10 @@ int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
     if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) p.split = atoi(e);
     else
       while (p.split < 4 && (long long)p.B * (1 + p.S) * ((p.H * 2 * p.split + kBandMax - 1) / kBandMax) <= 148 * 4) p.split *= 2;
+  }
+  {
+    const char* e = getenv("SFM_LIFO");           // development knob (see sfm_launch_fused)
+    p.interleave = (e && atoi(e) > 0) ? 1 : 0;
   }
   p.band = kBandMax / p.split;
   const int kBand = p.band;

@@ -26,6 +26,7 @@ struct StripTask {
 
 __device__ __forceinline__ StripTask decode_strip(const SfmFusedParams& p, int t) {
   StripTask k;
+  if (p.task_rev) t = p.task_begin[SFM_MAX_SCALES] - 1 - t;
   int s = 0;
 #pragma unroll
   for (int q = 1; q < SFM_MAX_SCALES; ++q)

@@ -41,17 +41,43 @@ def allreduce_loss_partials(losses, group=None, async_op=False):
 
 
 class ShardedViewSynthesisLoss(object):
-    """ViewSynthesisLoss over this rank's snippet shard; losses are completed by an allreduce."""
+    """ViewSynthesisLoss over this rank's snippet shard; losses are completed by an allreduce.
 
-    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None):
+    B_global: the batch every F.mean divides by.  When omitted it is the SUM of the local batches over the group
+    (one integer all-reduce at the first call), so uneven shards (shard_range gives e.g. 3 + 2) are normalised by
+    the true global batch.  Every other ViewSynthesisLoss keyword (raw_disp_scales, raw_pose, edge_aware_smooth,
+    n_scales) is forwarded."""
+
+    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None, **kwargs):
         from .functions import ViewSynthesisLoss
         self.group = group
-        self.op = ViewSynthesisLoss(smooth_reg, exp_reg, ssim_rate, B_global=B_global)
+        self.op = ViewSynthesisLoss(smooth_reg, exp_reg, ssim_rate, B_global=B_global, **kwargs)
+        self._explicit = B_global is not None
+        self._b_local = None                        # local batch the cached sum was taken for
 
-    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, async_op=False):
+    def _resolve_global_batch(self, src):
+        import torch
         import torch.distributed as dist
-        if self.op.B_global is None and dist.is_initialized():
-            self.op.B_global = int(src.shape[0]) * dist.get_world_size(self.group)
-        losses, grads = self.op.forward_backward(tgt, src, intrinsics, disps, poses, logits)
+        b_local = int(src.shape[0])
+        if b_local < 1:
+            raise ValueError('empty snippet shard: the global batch must be >= the world size')
+        if self._explicit:
+            if self.op.B_global < b_local:
+                raise ValueError('B_global=%d is smaller than the local batch %d' % (self.op.B_global, b_local))
+            return
+        if self._b_local == b_local:
+            return                                  # same shard size as last time: the cached sum stands
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dev = src.device if dist.get_backend(self.group) == 'nccl' else 'cpu'
+            t = torch.tensor([b_local], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.op.B_global = int(t.item())
+        else:
+            self.op.B_global = b_local
+        self._b_local = b_local
+
+    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, async_op=False, **kwargs):
+        self._resolve_global_batch(src)
+        losses, grads = self.op.forward_backward(tgt, src, intrinsics, disps, poses, logits, **kwargs)
         work = allreduce_loss_partials(losses, self.group, async_op=async_op)
         return losses, grads, work

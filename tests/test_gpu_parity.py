@@ -105,6 +105,53 @@ def test_loss_and_gradients_match_oracle(flagset, B, S, H, W, seed, harsh):
     np.testing.assert_allclose(host(grads['gdisps'][1]), 2.5 * ref[1], rtol=1e-6, atol=0)
 
 
+# BASELINE.json configs[3] (sfm_learner_v1_odom.yml:14-16, 5-frame snippets, 128x416) and configs[4] (256x832, SSIM
+# flags of sfm_learner_v1_ssim.yml:14-17) at their own shapes, with the launch variant the full batches pick
+# (B = 32: 8 runs per L1 task; B = 64: 64-row strips, one warp per SSIM task) forced through the development knobs.
+BIG_SHAPES = {
+    'cfg4': dict(flagset='v1_odom', B=2, S=4, H=128, W=416, seed=70, env={'SFM_HSEG': '8'}),
+    'cfg5': dict(flagset='v1_ssim', B=1, S=2, H=256, W=832, seed=71, env={'SFM_HSEG': '64', 'SFM_SSIM_NW': '1'}),
+}
+
+
+@pytest.mark.parametrize('cfg', sorted(BIG_SHAPES))
+def test_loss_and_gradients_match_oracle_at_cfg4_cfg5_shapes(cfg, monkeypatch):
+    c = BIG_SHAPES[cfg]
+    flags = FLAGSETS[c['flagset']]
+    d = make_snippets(c['B'], c['S'], c['H'], c['W'], seed=c['seed'])
+    L, G, _ = _oracle(d, flags)
+    g = dev_inputs(d)
+    for forced in (True, False):                     # the big-batch launch variant, then whatever the policy picks here
+        for k, v in c['env'].items():
+            monkeypatch.setenv(k, v) if forced else monkeypatch.delenv(k, raising=False)
+        losses, grads = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+        np.testing.assert_allclose(host(losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)
+        assert_grad_close(host(grads['gposes']), G['gpose'], what='gpose')
+        for s in range(4):
+            assert_grad_close(host(grads['gdisps'][s]), G['gdisp'][s], what='gdisp[%d]' % s)
+            if flags['exp_reg']:
+                assert_grad_close(host(grads['glogits'][s]), G['glogits'][s], what='glogits[%d]' % s)
+
+
+@pytest.mark.parametrize('cfg', sorted(BIG_SHAPES))
+def test_indices_masks_and_warp_bit_exact_at_cfg4_cfg5_shapes(cfg):
+    c = BIG_SHAPES[cfg]
+    flags = FLAGSETS[c['flagset']]
+    d = make_snippets(1, c['S'], c['H'], c['W'], seed=c['seed'] + 5, harsh=True)
+    proj, kinv = oracle_tables(O, d)
+    L, _, dbg = _oracle(d, flags, want_grads=False, want_debug=True,
+                        proj_override=np.concatenate([proj, np.zeros_like(proj[..., :1, :])], -2), kinv_override=kinv)
+    g = dev_inputs(d)
+    losses, gd = _op(flags).forward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'],
+                                    proj=to_dev(proj), kinv=to_dev(kinv), debug=True)
+    for s in range(4):
+        np.testing.assert_array_equal(host(gd['u0'][s]), dbg['u0'][s], err_msg='u0 scale %d' % s)
+        np.testing.assert_array_equal(host(gd['v0'][s]), dbg['v0'][s], err_msg='v0 scale %d' % s)
+        np.testing.assert_array_equal(host(gd['inb'][s]).astype(bool), dbg['inb'][s], err_msg='inb scale %d' % s)
+        np.testing.assert_array_equal(host(gd['P'][s]), dbg['P'][s], err_msg='warped image scale %d' % s)
+    np.testing.assert_allclose(host(losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.parametrize('name', ['v1', 'v1_ssim', 'v1_odom', 'v1_ssim_harsh', 'v1_odom_harsh'])
 def test_against_golden_fixtures(name):
     """CUDA path vs outputs of the reference's own source files (tests/golden/make_golden.py)."""

@@ -30,6 +30,20 @@ def _worker(rank, world, port, out_dir):
     work = allreduce_loss_partials(losses, async_op=True)
     work.wait()
     lo, hi = shard_range(B, rank, world)
+    # ShardedViewSynthesisLoss without B_global: the global batch is the SUM of the (uneven) local batches, not
+    # local * world (3 + 2 = 5, not 6 and 4); an explicit B_global is taken as is; an empty shard is rejected
+    from sfm_learner_chainer_b200.distributed import ShardedViewSynthesisLoss
+    sh = ShardedViewSynthesisLoss(0.1, 0.2, 0.0, edge_aware_smooth=True)
+    sh._resolve_global_batch(torch.from_numpy(mine['src']))
+    assert sh.op.B_global == B and sh.op.edge_aware_smooth, (sh.op.B_global, hi - lo)
+    sh2 = ShardedViewSynthesisLoss(0.1, 0.2, 0.0, B_global=7)
+    sh2._resolve_global_batch(torch.from_numpy(mine['src']))
+    assert sh2.op.B_global == 7
+    try:
+        sh._resolve_global_batch(torch.zeros(0, 2, 3, 32, 104))
+        raise AssertionError('empty shard accepted')
+    except ValueError:
+        pass
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), losses=losses.numpy(), gpose=G['gpose'], lo=lo, hi=hi,
              gdisp0=G['gdisp'][0])
     dist.destroy_process_group()
