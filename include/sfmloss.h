@@ -42,7 +42,8 @@ extern "C" {
 /* SfmDesc.flags */
 #define SFM_FLAG_TABLES_PROVIDED 0x1u /* caller supplies proj/kinv tables (bit-exact tests; the reference
                                          itself builds P on the host, transform.py:76-90) */
-#define SFM_FLAG_REUSE_PYRAMID 0x2u   /* workspace already holds this batch's image pyramid */
+#define SFM_FLAG_REUSE_PYRAMID 0x2u   /* workspace already holds this batch's image pyramid (sfm_pyramid); in->tgt / in->src
+                                         are still read (scale 0 is never copied) */
 #define SFM_FLAG_NO_TMA 0x4u          /* reserved (accepted and ignored: the marching kernels stage nothing through TMA) */
 #define SFM_FLAG_EDGE_AWARE_SMOOTH 0x8u /* the smoothness term is compute_disp_smooth(curr_tgt_img, pred_disps[ns])
                                          (base_model.py:144-155), the edge-aware alternative the reference keeps
@@ -124,9 +125,9 @@ typedef struct SfmDebug {
 int sfm_version(void);
 const char* sfm_last_error(void);
 
-/* Bytes of device scratch a call needs (image pyramid in NHWC4, projection tables, fp64 reduction
- * cells).  The caller allocates it (any 256-byte aligned device pointer) and passes it to every call
- * with the same descriptor. */
+/* Bytes of device scratch a call needs (image pyramid of the scales >= 1, planar like the inputs; projection
+ * tables; fp64 reduction cells).  The caller allocates it (any 256-byte aligned device pointer) and passes it to
+ * every call with the same descriptor.  Scale 0 is read straight from in->tgt / in->src. */
 size_t sfm_workspace_bytes(const SfmDesc* desc);
 
 /* losses_out: device float[5] = total, pixel, smooth, exp, ssim  (chainer.report keys,
@@ -157,9 +158,9 @@ int sfm_scale_grads(const SfmDesc* desc, const float* gy, const SfmGrads* grads,
  * kernel, on the call's stream.  Pass NULL, NULL to clear. */
 int sfm_set_kernel_events(void* start_event, void* stop_event);
 
-/* Image pyramid only (F.resize_images from full resolution, base_model.py:70-72) into the workspace;
- * sfm_pyramid_export copies one level back out as NCHW for tests:
- * tgt_out (B,3,h,w), src_out (B,S,3,h,w). */
+/* Image pyramid only (F.resize_images from full resolution, base_model.py:70-72; scales 1..n_scales-1, scale 0 is
+ * the identity and is never copied) into the workspace; sfm_pyramid_export copies one level (scale >= 1) back
+ * out for tests: tgt_out (B,3,h,w), src_out (B,S,3,h,w). */
 int sfm_pyramid(const SfmDesc* desc, const float* tgt, const float* src, void* workspace, void* stream);
 int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, int scale, float* tgt_out, float* src_out,
                        void* stream);

@@ -144,8 +144,8 @@ int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyr
   p.build_tables = (d->flags & SFM_FLAG_TABLES_PROVIDED) ? 0 : 1;
   p.tgt = in->tgt; p.src = in->src; p.intrinsics = in->intrinsics; p.poses = in->poses;
   for (int s = 0; s < d->n_scales; ++s) {
-    p.tgt_pyr[s] = (float4*)(ws + L.off_tgt[s]);
-    p.src_pyr[s] = (float4*)(ws + L.off_src[s]);
+    p.tgt_pyr[s] = (float*)(ws + L.off_tgt[s]);
+    p.src_pyr[s] = (float*)(ws + L.off_src[s]);
   }
   p.proj_out = (float*)(ws + L.off_proj);
   p.kinv_out = (float*)(ws + L.off_kinv);
@@ -162,7 +162,7 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   int rc = sfm_validate_desc(d);
   if (rc) return rc;
   const bool reuse = (d->flags & SFM_FLAG_REUSE_PYRAMID) != 0;
-  rc = check_inputs(d, in, !reuse);
+  rc = check_inputs(d, in, true);      // the images are always needed: scale 0 is read from the caller's tensors
   if (rc) return rc;
   if (grads && (rc = check_grads(d, grads))) return rc;
   if (!workspace) { sfm_set_error("workspace is NULL"); return SFM_E_NULL_POINTER; }
@@ -185,8 +185,8 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   for (int s = 0; s < d->n_scales; ++s) {
     const int h = d->H >> s, w = d->W >> s;
     p.h[s] = h; p.w[s] = w;
-    p.tgt_pyr[s] = (const float4*)(ws + L.off_tgt[s]);
-    p.src_pyr[s] = (const float4*)(ws + L.off_src[s]);
+    p.tgt_pl[s] = s == 0 ? in->tgt : (const float*)(ws + L.off_tgt[s]);
+    p.src_pl[s] = s == 0 ? in->src : (const float*)(ws + L.off_src[s]);
     p.disp[s] = in->disps[s];
     p.logits[s] = m.use_exp ? in->logits[s] : nullptr;
     p.gdisp[s] = grads ? grads->gdisps[s] : nullptr;
@@ -279,8 +279,8 @@ extern "C" int sfm_pyramid(const SfmDesc* desc, const float* tgt, const float* s
   p.do_pyramid = 1; p.build_tables = 0;
   p.tgt = tgt; p.src = src;
   for (int s = 0; s < desc->n_scales; ++s) {
-    p.tgt_pyr[s] = (float4*)(ws + L.off_tgt[s]);
-    p.src_pyr[s] = (float4*)(ws + L.off_src[s]);
+    p.tgt_pyr[s] = (float*)(ws + L.off_tgt[s]);
+    p.src_pyr[s] = (float*)(ws + L.off_src[s]);
   }
   p.acc = (double*)(ws + L.off_acc);
   p.n_acc = 0;
@@ -292,14 +292,19 @@ extern "C" int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, in
                                   float* src_out, void* stream) {
   int rc = sfm_validate_desc(desc);
   if (rc) return rc;
-  if (scale < 0 || scale >= desc->n_scales) { sfm_set_error("sfm_pyramid_export: scale %d out of range", scale); return SFM_E_INVALID_DESC; }
+  if (scale < 1 || scale >= desc->n_scales) {
+    sfm_set_error("sfm_pyramid_export: scale %d out of range (the workspace holds scales 1..%d; scale 0 is the input itself)", scale,
+                  desc->n_scales - 1);
+    return SFM_E_INVALID_DESC;
+  }
   if (!workspace) { sfm_set_error("sfm_pyramid_export: null workspace"); return SFM_E_NULL_POINTER; }
   SfmWsLayout L;
   sfm_ws_layout(desc, &L);
   const char* ws = (const char*)workspace;
-  const int h = desc->H >> scale, w = desc->W >> scale;
-  if (tgt_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_tgt[scale]), tgt_out, desc->B, h, w, 0, (cudaStream_t)stream))) return rc;
-  if (src_out && (rc = sfm_launch_pyramid_export((const float4*)(ws + L.off_src[scale]), src_out, (long long)desc->B * desc->S, h, w, 1, (cudaStream_t)stream))) return rc;
+  // the pyramid levels are stored exactly in the output layout: (B,3,h,w) and (B,S,3,h,w)
+  const size_t lvl = (size_t)3 * (desc->H >> scale) * (desc->W >> scale) * sizeof(float);
+  if (tgt_out) SFM_CUDA_CHECK(cudaMemcpyAsync(tgt_out, ws + L.off_tgt[scale], desc->B * lvl, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (src_out) SFM_CUDA_CHECK(cudaMemcpyAsync(src_out, ws + L.off_src[scale], (size_t)desc->B * desc->S * lvl, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

@@ -31,8 +31,10 @@ void sfm_set_error(const char* fmt, ...);
 // workspace layout (host + device agree through this struct)
 // ---------------------------------------------------------------------------------------------
 struct SfmWsLayout {
-  size_t off_tgt[SFM_MAX_SCALES];  // float4 [B][h][w]            target pyramid, NHWC4 (RGB + pad), dense
-  size_t off_src[SFM_MAX_SCALES];  // float4 [B*S][h+2][w+1]      source pyramid, NHWC4, zero-padded (see below)
+  // Image pyramid, scales >= 1 only: planar fp32 exactly like the caller's tensors ([img][3][h][w], no padding).
+  // Scale 0 is the identity of F.resize_images and is read straight from the caller's tgt / src tensors.
+  size_t off_tgt[SFM_MAX_SCALES];  // float [B][3][h][w]
+  size_t off_src[SFM_MAX_SCALES];  // float [B*S][3][h][w]
   size_t off_proj;                 // float  [B][S][ns][12]  3x4 projection K4.T
   size_t off_kinv;                 // float  [B][ns][9]
   size_t off_acc;                  // double [4 + B*S*ns*12] loss sums (pixel, smooth, exp, ssim) + dL/dP per scale
@@ -42,18 +44,11 @@ struct SfmWsLayout {
   size_t total;
 };
 
-// Source pyramid padding: every row carries one extra zero texel (pitch = w+1) and every image two extra
-// zero rows.  A strictly in-bounds sample has u in (0, w-1], v in (0, h-1]; when u == w-1 (or v == h-1)
-// exactly, the taps at u0+1 == w (v0+1 == h) are zero-padding taps of F.spatial_transformer_sampler and
-// read the zero texels, so the gather needs no validity logic at all.  Out-of-view pixels are pointed at
-// the two zero rows (row h), which makes their warped value exactly 0 (base_model.py:96's mask rule).
 #ifdef __CUDACC__
 #define SFM_HD __host__ __device__
 #else
 #define SFM_HD
 #endif
-static inline SFM_HD int sfm_src_pitch(int w) { return w + 1; }
-static inline SFM_HD int sfm_src_rows(int h) { return h + 2; }
 
 static inline size_t sfm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -62,12 +57,12 @@ static inline void sfm_ws_layout(const SfmDesc* d, SfmWsLayout* L) {
   for (int s = 0; s < SFM_MAX_SCALES; ++s) {
     L->off_tgt[s] = L->off_src[s] = 0;
   }
-  for (int s = 0; s < d->n_scales; ++s) {
+  for (int s = 1; s < d->n_scales; ++s) {
     const int h = d->H >> s, w = d->W >> s;
     L->off_tgt[s] = off;
-    off = sfm_align_up(off + (size_t)d->B * h * w * 16, 256);
+    off = sfm_align_up(off + (size_t)d->B * 3 * h * w * sizeof(float), 256);
     L->off_src[s] = off;
-    off = sfm_align_up(off + (size_t)d->B * d->S * sfm_src_rows(h) * sfm_src_pitch(w) * 16, 256);
+    off = sfm_align_up(off + (size_t)d->B * d->S * 3 * h * w * sizeof(float), 256);
   }
   L->off_proj = off;
   off = sfm_align_up(off + (size_t)d->B * d->S * d->n_scales * 12 * sizeof(float), 256);

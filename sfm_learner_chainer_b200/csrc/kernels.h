@@ -13,8 +13,8 @@ struct SfmPrepParams {
   const float* src;
   const float* intrinsics;
   const float* poses;
-  float4* tgt_pyr[SFM_MAX_SCALES];
-  float4* src_pyr[SFM_MAX_SCALES];
+  float* tgt_pyr[SFM_MAX_SCALES];   // planar [B][3][h][w], written for scales >= 1 only
+  float* src_pyr[SFM_MAX_SCALES];   // planar [B*S][3][h][w]
   float* proj_out;
   float* kinv_out;
   double* acc;
@@ -27,7 +27,6 @@ struct SfmPrepParams {
   int n_pyr_blocks;
   int vec0;          // scale 0 copied 4 pixels per thread
   int band, split;   // full-resolution rows per pyramid CTA; warps sharing one row
-  int interleave;    // 1: CTAs ordered snippet by snippet (target, then its sources) instead of all targets first
 };
 
 int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
@@ -38,7 +37,6 @@ int sfm_launch_eval_depth(int B, int h, int w, int Hg, int Wg, const float* pred
                           float hi, float* out, void* scratch, cudaStream_t stream);
 int sfm_launch_disp_activation(long long n, const float* x, float* disp, float* dact, cudaStream_t stream);
 int sfm_launch_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, cudaStream_t stream);
-int sfm_launch_pyramid_export(const float4* pyr, float* out, long long n_img, int h, int w, int padded, cudaStream_t stream);
 
 // Fused loss kernel parameters (one launch covers every scale, source and snippet).
 struct SfmFusedParams {
@@ -52,12 +50,12 @@ struct SfmFusedParams {
   int hseg;
   int nstrip[SFM_MAX_SCALES], nseg[SFM_MAX_SCALES];
   int task_begin[SFM_MAX_SCALES + 1];
-  int task_rev;      // 1: tasks are walked from the last to the first (the pyramid of the last snippets is the warmest in L2)
-  int pf_tasks;      // > 0: every L1 task prefetches (to L2) the source texels of the task pf_tasks ahead
   float wm1f[SFM_MAX_SCALES], hm1f[SFM_MAX_SCALES];   // (float)(w-1), (float)(h-1)
   float hwf[SFM_MAX_SCALES], hhf[SFM_MAX_SCALES];     // (w-1)/2, (h-1)/2
-  const float4* tgt_pyr[SFM_MAX_SCALES];
-  const float4* src_pyr[SFM_MAX_SCALES];
+  // images of every scale, planar fp32 [img][3][h][w]: scale 0 = the caller's tgt / src tensors themselves, scales >= 1 =
+  // the pyramid in the workspace
+  const float* tgt_pl[SFM_MAX_SCALES];
+  const float* src_pl[SFM_MAX_SCALES];
   const float* disp[SFM_MAX_SCALES];
   const float* logits[SFM_MAX_SCALES];
   float* gdisp[SFM_MAX_SCALES];

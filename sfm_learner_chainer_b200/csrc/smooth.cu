@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) sfm_edge_smooth_kernel(const __grid_const
   const int h = p.h[s], w = p.w[s], plane = h * w;
   const bool raw = (p.raw_disp_mask >> s) & 1u;
   const float* __restrict__ D = p.disp[s] + (size_t)b * plane;
-  const float4* __restrict__ T = p.tgt_pyr[s] + (size_t)b * plane;
+  const float* __restrict__ T = p.tgt_pl[s] + (size_t)b * 3 * plane;      // planar (3, h, w)
   float* __restrict__ G = GRAD ? p.gdisp[s] + (size_t)b * plane : nullptr;
   const float kx = p.sm_ex[s], ky = p.sm_ey[s];
   const float gyv = (GRAD && p.gy) ? __ldg(p.gy) : 1.f;
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(256) sfm_edge_smooth_kernel(const __grid_const
     return raw ? sfm_disp_act(v, f) : v;
   };
   // exp(-|mean_c (b - a)|): F.mean over the three channels = ((d0 + d1) + d2) / 3, F.absolute, F.exp
-  auto edge = [&](const float4& a, const float4& c) {
+  struct Px { float x, y, z; };
+  auto tex = [&](int i) { Px v; v.x = __ldg(T + i); v.y = __ldg(T + plane + i); v.z = __ldg(T + 2 * plane + i); return v; };
+  auto edge = [&](const Px& a, const Px& c) {
     const float m = __fdiv_rn(__fadd_rn(__fadd_rn(__fsub_rn(c.x, a.x), __fsub_rn(c.y, a.y)), __fsub_rn(c.z, a.z)), 3.f);
     return expf(-fabsf(m));
   };
@@ -160,21 +162,21 @@ __global__ void __launch_bounds__(256) sfm_edge_smooth_kernel(const __grid_const
     const int y = i / w, x = i - y * w;
     float f0, fd;
     const float d0 = disp_at(i, f0);
-    const float4 t0 = __ldg(T + i);
+    const Px t0 = tex(i);
     float g = 0.f;
     if (x + 1 < w) {
-      const float dd = __fsub_rn(disp_at(i + 1, fd), d0), e = edge(t0, __ldg(T + i + 1));
+      const float dd = __fsub_rn(disp_at(i + 1, fd), d0), e = edge(t0, tex(i + 1));
       loss += fabsf(dd) * e * kx;
       g -= sgnc(dd, kx) * e;
     }
     if (y + 1 < h) {
-      const float dd = __fsub_rn(disp_at(i + w, fd), d0), e = edge(t0, __ldg(T + i + w));
+      const float dd = __fsub_rn(disp_at(i + w, fd), d0), e = edge(t0, tex(i + w));
       loss += fabsf(dd) * e * ky;
       g -= sgnc(dd, ky) * e;
     }
     if (GRAD) {
-      if (x > 0) g += sgnc(__fsub_rn(d0, disp_at(i - 1, fd)), kx) * edge(__ldg(T + i - 1), t0);
-      if (y > 0) g += sgnc(__fsub_rn(d0, disp_at(i - w, fd)), ky) * edge(__ldg(T + i - w), t0);
+      if (x > 0) g += sgnc(__fsub_rn(d0, disp_at(i - 1, fd)), kx) * edge(tex(i - 1), t0);
+      if (y > 0) g += sgnc(__fsub_rn(d0, disp_at(i - w, fd)), ky) * edge(tex(i - w), t0);
       G[i] = raw ? (gyv * g) * f0 : gyv * g;
     }
   }

@@ -26,7 +26,6 @@ struct StripTask {
 
 __device__ __forceinline__ StripTask decode_strip(const SfmFusedParams& p, int t) {
   StripTask k;
-  if (p.task_rev) t = p.task_begin[SFM_MAX_SCALES] - 1 - t;
   int s = 0;
 #pragma unroll
   for (int q = 1; q < SFM_MAX_SCALES; ++q)
@@ -75,6 +74,16 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
   __shared__ float sG[(NW > 1) ? 3 * 2 * 32 : 1];       // [ring slot][gdd | dsc][lane] of warp 1's row term
   const int wi = (NW > 1) ? (int)(threadIdx.x >> 5) : 0;
   float4* const sP = sP_all[wi];
+  // warp-uniform base pointers, re-read (broadcast LDS.64) where they are used: at 168 registers ptxas otherwise
+  // re-derives them from the kernel parameters inside the row loop (64-bit multiplies per row, seen in the SASS)
+  struct RowPtrs {
+    const float* img;
+    const float* tgt;
+    const float* disp;
+    float* gdisp;
+  };
+  __shared__ RowPtrs s_ptrs_all[NW];
+  volatile RowPtrs* const pp = &s_ptrs_all[wi];
   // two-row delay line of forward records: [slot][field][lane], written in stage A of row r and read back by
   // the same lane in stages E/F two steps later (no synchronisation needed).  In registers these 51 values
   // pushed the kernel over its 168-register budget (17-27 local-memory spills per three rows).
@@ -106,9 +115,9 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
   const float rxx = __fmul_rn(kk0, xf), ryx = __fmul_rn(kk3, xf), rzx = __fmul_rn(kk6, xf);
   const int plane = h * w;
   const float* __restrict__ disp = p.disp[s] + (size_t)b * plane;
-  const float4* __restrict__ tgt = p.tgt_pyr[s] + (size_t)b * plane;
+  const float* __restrict__ tgt = p.tgt_pl[s] + (size_t)b * 3 * plane;
   float* __restrict__ gdisp = GRAD ? p.gdisp[s] + (size_t)b * plane : nullptr;
-  const size_t src_img = (size_t)sfm_src_rows(h) * geo.pitch;
+  const size_t src_img = (size_t)3 * plane;
   float pix_part = 0.f, ssim_part = 0.f;
   const int r_begin = t.y0 - 2, r_end = t.y1 + 2;      // rows [r_begin, r_end) are warped
   const bool opaque_true = p.hseg != 0x7fffffff;       // always true, unknown to ptxas: basic-block fence (see step)
@@ -121,13 +130,19 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
     float accA[3] = {0.f, 0.f, 0.f}, accB[3] = {0.f, 0.f, 0.f}, accC[3] = {0.f, 0.f, 0.f};
     const bool first = (i == 0);
     const bool writer = (NW == 1) || (wi == 0);          // the warp that loads / stores gdisp
-    const float4* __restrict__ img = p.src_pyr[s] + ((size_t)b * S + i) * src_img;
+    if (lane == 0) {
+      s_ptrs_all[wi].img = p.src_pl[s] + ((size_t)b * S + i) * src_img;
+      s_ptrs_all[wi].tgt = tgt;
+      s_ptrs_all[wi].disp = disp;
+      s_ptrs_all[wi].gdisp = gdisp;
+    }
+    __syncwarp();
     // rings: window row sums (P, P^2, P.T, T, T^2 per channel), gradient-field row sums, forward records
     float hs[3][15], gs[3][9];
     Rec rec[3];
     bool mask[3];                                        // all-zero mask of the row's pixel (base_model.py:96)
     float dq[3];                                         // disparity / target rows fetched ahead
-    float4 Tq[3];
+    float Tq[3][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -143,18 +158,22 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
         for (int q = 0; q < 18; ++q) myrec[(k * 18 + q) * 32] = 0.f;
       }
       dq[k] = 1.f;
-      Tq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      Tq[k][0] = Tq[k][1] = Tq[k][2] = 0.f;
     }
-    auto load_dT = [&](int r, float& dd, float4& TT) {
+    auto load_dT = [&](int r, float& dd, float* TT) {
       dd = 1.f;
-      TT = make_float4(0.f, 0.f, 0.f, 0.f);
+      TT[0] = TT[1] = TT[2] = 0.f;
       if (col_in && (r >= 0) && (r < h) && (r < r_end)) {
-        dd = __ldg(disp + r * w + xx);
-        TT = __ldg(tgt + r * w + xx);
+        const unsigned o = (unsigned)(r * w + xx);
+        const float* tb = pp->tgt;
+        dd = __ldg(pp->disp + o);
+        TT[0] = __ldg(tb + o);
+        TT[1] = __ldg(tb + (o + geo.plane));
+        TT[2] = __ldg(tb + (o + 2u * geo.plane));
       }
     };
     // pending row: projected, gathers in flight, consumed by the next step
-    float4 I00, I01, I10, I11;
+    Taps I;
     float pwa = 0.f, pwb = 0.f, pwc = 0.f, pwd = 0.f, pq0 = 0.f, pq1 = 0.f, pq2 = 0.f, pr = 0.f, pdepth = 0.f, pdsc = 0.f;
     float g_old = 0.f;
 
@@ -183,22 +202,18 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
       pair_project(P, X, Y, Z, geo, f, in_img);
       pwa = f.wa; pwb = f.wb; pwc = f.wc; pwd = f.wd;
       pq0 = f.q0; pq1 = f.q1; pq2 = f.q2; pr = f.r;
-      const float4* __restrict__ tp = img + f.idx;
-      I00 = __ldg(tp);
-      I01 = __ldg(tp + 1);
-      I10 = __ldg(tp + geo.pitch);
-      I11 = __ldg(tp + geo.pitch + 1);
+      gather_taps(pp->img, geo, f, I);
       load_dT(r + 1, dq[nx], Tq[nx]);
       if (GRAD && (ACCUM || !first) && writer) {
         const int rf = r - 2;
-        g_old = (col_own && rf >= t.y0 && rf < t.y1) ? gdisp[rf * w + xx] : 0.f;
+        g_old = (col_own && rf >= t.y0 && rf < t.y1) ? ld_global(pp->gdisp + (unsigned)(rf * w + xx)) : 0.f;
       }
       if (DEBUG && in_img && col_own && (r >= t.y0) && (r < t.y1) && p.dbg_u0[s]) {
         const size_t o = ((size_t)b * S + i) * plane + (size_t)r * w + xx;
         SfmCoord c;
         sfm_project(P, X, Y, Z, w, h, geo.hw, geo.hh, c);
-        p.dbg_u0[s][o] = f.inb ? (int)(f.idx % (unsigned)geo.pitch) : c.u0;
-        p.dbg_v0[s][o] = f.inb ? (int)(f.idx / (unsigned)geo.pitch) : c.v0;
+        p.dbg_u0[s][o] = f.inb ? (int)(f.idx % (unsigned)w) : c.u0;
+        p.dbg_v0[s][o] = f.inb ? (int)(f.idx / (unsigned)w) : c.v0;
         p.dbg_inb[s][o] = f.inb ? 1 : 0;
       }
     };
@@ -211,25 +226,24 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
       // ---------------- stage A: blend pixel (r, lane) from the taps gathered during the previous step
       Rec& rc_ = rec[cur];
       {
-        const float4 T = Tq[cur];
+        const float* T = Tq[cur];
         const float w1 = __fmul_rn(pwa, pwc), w2 = __fmul_rn(pwb, pwc);
         const float w3 = __fmul_rn(pwa, pwd), w4 = __fmul_rn(pwb, pwd);
-        const float P0 = sfm_blend(w1, w2, w3, w4, I00.x, I01.x, I10.x, I11.x);
-        const float P1 = sfm_blend(w1, w2, w3, w4, I00.y, I01.y, I10.y, I11.y);
-        const float P2 = sfm_blend(w1, w2, w3, w4, I00.z, I01.z, I10.z, I11.z);
+        const float P0 = sfm_blend(w1, w2, w3, w4, I.a[0], I.b[0], I.c[0], I.d[0]);
+        const float P1 = sfm_blend(w1, w2, w3, w4, I.a[1], I.b[1], I.c[1], I.d[1]);
+        const float P2 = sfm_blend(w1, w2, w3, w4, I.a[2], I.b[2], I.c[2], I.d[2]);
         const bool m = (P0 == 0.f) && (P1 == 0.f) && (P2 == 0.f);               // true outside the image / view
         const bool own = col_own && (r >= t.y0) && (r < t.y1);
-        pix_part += (own && !m) ? (fabsf(P0 - T.x) + fabsf(P1 - T.y) + fabsf(P2 - T.z)) : 0.f;
+        pix_part += (own && !m) ? (fabsf(P0 - T[0]) + fabsf(P1 - T[1]) + fabsf(P2 - T[2])) : 0.f;
         mask[cur] = m;
         rc_.P[0] = P0; rc_.P[1] = P1; rc_.P[2] = P2;
-        rc_.T[0] = T.x; rc_.T[1] = T.y; rc_.T[2] = T.z;
+        rc_.T[0] = T[0]; rc_.T[1] = T[1]; rc_.T[2] = T[2];
         if (GRAD) {
-          rc_.Ix[0] = pwc * (I01.x - I00.x) + pwd * (I11.x - I10.x);
-          rc_.Ix[1] = pwc * (I01.y - I00.y) + pwd * (I11.y - I10.y);
-          rc_.Ix[2] = pwc * (I01.z - I00.z) + pwd * (I11.z - I10.z);
-          rc_.Iy[0] = pwa * (I10.x - I00.x) + pwb * (I11.x - I01.x);
-          rc_.Iy[1] = pwa * (I10.y - I00.y) + pwb * (I11.y - I01.y);
-          rc_.Iy[2] = pwa * (I10.z - I00.z) + pwb * (I11.z - I01.z);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            rc_.Ix[c] = pwc * (I.b[c] - I.a[c]) + pwd * (I.d[c] - I.c[c]);
+            rc_.Iy[c] = pwa * (I.c[c] - I.a[c]) + pwb * (I.d[c] - I.b[c]);
+          }
           rc_.q0 = pq0; rc_.q1 = pq1; rc_.q2 = pq2; rc_.r = pr;
           rc_.depth = pdepth;
           rc_.dsc = RAW ? pdsc : pdepth;
@@ -246,11 +260,6 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
             if (RAW) o[17 * 32] = pdsc;
           }
         }
-#if SFM_USE_PAD
-        pix_part += pad_sum(I00, I01, I10, I11, T);
-#else
-        keep_live(I00.w); keep_live(I01.w); keep_live(I10.w); keep_live(I11.w); keep_live(T.w);
-#endif
         if (DEBUG && own && p.dbg_P[s]) {
           float* o = p.dbg_P[s] + ((size_t)b * S + i) * 3 * plane + (size_t)r * w + xx;
           o[0] = P0;
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
         accA[0] += e0; accA[1] += e1; accA[2] += e2;
         accB[0] = fmaf(e0, yfb, accB[0]); accB[1] = fmaf(e1, yfb, accB[1]); accB[2] = fmaf(e2, yfb, accB[2]);
         accC[0] += gq0; accC[1] += gq1; accC[2] += gq2;
-        float* gp = gdisp + rf * w + xx;
+        float* gp = pp->gdisp + (unsigned)(rf * w + xx);
         float gval = g_prev - gdd * rb.dsc;
         if (NW > 1) {
           // warp 1 -> warp 0: (gdd, dsc) of the second source for this row; warp 0 continues the sequential chain
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
           __syncthreads();
           if (wi == 0) gval = gval - slot[0] * slot[32];
         }
-        if (do_f && writer) *gp = gval;
+        if (do_f && writer) st_global(gp, gval);
       }
 #if SFM_SSIM_FENCE
       }

@@ -75,6 +75,31 @@ def current_stream(like):
     return 0
 
 
+def record_event(like):
+    """Event recorded on the caller's current stream (None for carriers without a stream API)."""
+    if is_torch(like):
+        ev = _torch().cuda.Event()
+        ev.record(_torch().cuda.current_stream(like.device))
+        return ev
+    if is_cupy(like):
+        import cupy
+        ev = cupy.cuda.Event()
+        ev.record(cupy.cuda.get_current_stream())
+        return ev
+    return None
+
+
+def wait_event(like, ev):
+    """Makes the caller's current stream wait for `ev` (no host synchronisation)."""
+    if ev is None:
+        return
+    if is_torch(like):
+        _torch().cuda.current_stream(like.device).wait_event(ev)
+    elif is_cupy(like):
+        import cupy
+        cupy.cuda.get_current_stream().wait_event(ev)
+
+
 def to_numpy(a):
     if is_torch(a):
         return a.detach().cpu().numpy()

@@ -38,6 +38,8 @@ class ViewSynthesisLoss(object):
         self.B_global = B_global
         self._lib = L.load()
         self._ws = {}
+        self._ev_pyramid = None      # build_pyramid done (the loss call waits for it when it reuses the pyramid)
+        self._ev_loss = None         # last loss call done with the workspace (the next build_pyramid waits for it)
 
     # ---- helpers
     @property
@@ -148,15 +150,21 @@ class ViewSynthesisLoss(object):
         return out
 
     def build_pyramid(self, tgt, src):
-        """F.resize_images pyramid of this batch (base_model.py:70-72) into the operator's workspace.  It depends
-        on the input images alone, so a trainer can issue it for the next batch on a side stream while the CNNs
-        run; the following forward_backward(..., reuse_pyramid=True) then only builds the projection tables."""
+        """F.resize_images pyramid of this batch (base_model.py:70-72; scales >= 1, scale 0 is the input itself) into
+        the operator's workspace.  It depends on the input images alone, so it can be issued as soon as the batch is
+        on the device; the following forward_backward(..., reuse_pyramid=True) -- with the SAME tgt / src tensors,
+        which it still reads at scale 0 -- then only builds the projection tables.
+        May be issued on a side stream: the operator records an event here that the reusing loss call waits for,
+        and the loss call records one that the next build_pyramid waits for.  The workspace is a single buffer, so
+        one batch is in flight per operator; use one operator per in-flight batch to overlap more."""
         B, S, _, H, W = src.shape
         D.check_array(tgt, 'tgt_img', (B, 3, H, W))
         D.check_array(src, 'src_imgs', (B, S, 3, H, W))
         desc = self._desc(B, S, H, W)
+        D.wait_event(tgt, self._ev_loss)           # a loss call on another stream may still be reading the workspace
         L.check(self._lib.sfm_pyramid(C.byref(desc), _vp(tgt), _vp(src), self._workspace(desc, tgt),
                                       C.c_void_p(D.current_stream(tgt))))
+        self._ev_pyramid = D.record_event(tgt)
 
     def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, proj=None, kinv=None, reuse_pyramid=False):
         """Single fused pass: -> (losses (5,), dict(gdisps, gposes, glogits)) for upstream gradient 1.
@@ -164,11 +172,14 @@ class ViewSynthesisLoss(object):
         desc, inp = self._pack(tgt, src, intrinsics, disps, poses, logits, proj, kinv)
         if reuse_pyramid:
             desc.flags |= L.SFM_FLAG_REUSE_PYRAMID
+            D.wait_event(tgt, self._ev_pyramid)     # build_pyramid may have run on another stream
         g, out = self._alloc_grads(desc, tgt)
         losses = D.empty(tgt, (5,))
         L.check(self._lib.sfm_loss_forward_backward(C.byref(desc), C.byref(inp), _vp(losses), C.byref(g),
                                                     self._workspace(desc, tgt),
                                                     C.c_void_p(D.current_stream(tgt))))
+        if self._ev_pyramid is not None:
+            self._ev_loss = D.record_event(tgt)
         return losses, out
 
     def scale_grads(self, grads, gy, B, S, H, W):
@@ -194,8 +205,8 @@ class ViewSynthesisLoss(object):
         ws = self._workspace(desc, tgt)
         st = C.c_void_p(D.current_stream(tgt))
         L.check(self._lib.sfm_pyramid(C.byref(desc), _vp(tgt), _vp(src), ws, st))
-        tp, sp = [], []
-        for s in range(self.n_scales):
+        tp, sp = [tgt], [src]                     # scale 0 is the identity of resize_images: the inputs themselves
+        for s in range(1, self.n_scales):
             t = D.empty(tgt, (B, 3, H >> s, W >> s))
             r = D.empty(tgt, (B, S, 3, H >> s, W >> s))
             L.check(self._lib.sfm_pyramid_export(C.byref(desc), ws, s, _vp(t), _vp(r), st))

@@ -40,9 +40,8 @@ def test_workspace_and_validation(lib):
     so = lib.load()
     d = lib.SfmDesc(4, 2, 128, 416, 4, 0, 0.1, 0.0, 0.15, 0)
     n = so.sfm_workspace_bytes(C.byref(d))
-    pyr = 4 * 3 * 70720 * 16          # dense NHWC4 pyramid; the source levels carry a zero border (w+1, h+2)
-    pad = 4 * 2 * sum(((128 >> s) + 2) * ((416 >> s) + 1) - (128 >> s) * (416 >> s) for s in range(4)) * 16
-    assert pyr + pad <= n <= pyr + pad + 64 * 1024
+    pyr = 4 * 3 * (70720 - 128 * 416) * 12      # planar fp32 pyramid of the scales >= 1 (scale 0 is never copied)
+    assert pyr <= n <= pyr + 64 * 1024
     for bad, code in [(lib.SfmDesc(0, 2, 128, 416, 4, 0, 0, 0, 0, 0), 'B=0'),
                       (lib.SfmDesc(4, 9, 128, 416, 4, 0, 0, 0, 0, 0), 'S=9'),
                       (lib.SfmDesc(4, 2, 16, 416, 4, 0, 0, 0, 0, 0), '2x52'),

@@ -510,6 +510,36 @@ def test_reuse_pyramid_flag(flagset):
         np.testing.assert_array_equal(host(g1['gdisps'][s]), host(g0['gdisps'][s]))
 
 
+def test_pyramid_built_on_a_side_stream_is_ordered_by_the_operator():
+    """build_pyramid on a side stream, the reusing loss call on the main stream, alternating batches through ONE
+    operator (one workspace): the operator's own events must order pyramid -> loss -> next pyramid, so every
+    result equals the all-in-one call bit for bit."""
+    import torch
+    flags = FLAGSETS['v1_ssim']
+    sets = [dev_inputs(make_snippets(4, 2, 128, 416, seed=80 + k)) for k in range(2)]
+    ref = []
+    for g in sets:
+        l, gr = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+        ref.append((host(l), [host(x) for x in gr['gdisps']], host(gr['gposes'])))
+    op = _op(flags)
+    side = torch.cuda.Stream()
+    outs = []
+    torch.cuda.synchronize()
+    for it in range(12):
+        g = sets[it & 1]
+        with torch.cuda.stream(side):
+            op.build_pyramid(g['tgt'], g['src'])
+        outs.append(op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'],
+                                        reuse_pyramid=True))
+    torch.cuda.synchronize()
+    for it, (l, gr) in enumerate(outs):
+        rl, rg, rp = ref[it & 1]
+        np.testing.assert_array_equal(host(l), rl)
+        np.testing.assert_array_equal(host(gr['gposes']), rp)
+        for s in range(4):
+            np.testing.assert_array_equal(host(gr['gdisps'][s]), rg[s])
+
+
 @pytest.mark.parametrize('flagset', ['v1', 'v1_ssim', 'v1_odom'])
 @pytest.mark.parametrize('B,S,H,W', [(1, 1, 32, 32),      # one source view, smallest legal size (4x4 at the coarsest scale)
                                      (3, 3, 36, 60),      # odd source count, sizes that are not multiples of 8 (4x7 at scale 3)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2b_pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/r2b_pytest_gpu.log
+timeout 600 python tools/exp_variants.py cfg1 cfg2 cfg4 cfg5 -- "" 2>&1 | tee gpurun_out/r2b_time.log
