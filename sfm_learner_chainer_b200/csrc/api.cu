@@ -134,7 +134,8 @@ int check_grads(const SfmDesc* d, const SfmGrads* g) {
   return 0;
 }
 
-int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyramid, cudaStream_t st) {
+int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyramid, const SfmSmoothParams* sm, int sm_mode,
+             cudaStream_t st) {
   SfmWsLayout L;
   sfm_ws_layout(d, &L);
   char* ws = (char*)workspace;
@@ -154,7 +155,7 @@ int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyr
   p.counter = (unsigned*)(ws + L.off_counter);
   p.raw_pose_hw = d->raw_pose_hw;
   p.posevec_out = (float*)(ws + L.off_posevec);
-  return sfm_launch_prep(p, st);
+  return sfm_launch_prep(p, sm, sm_mode, st);
 }
 
 int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const SfmGrads* grads, const float* gy,
@@ -172,9 +173,6 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
     sfm_set_error("no CUDA device: libsfmloss has no CPU fallback");
     return SFM_E_NO_DEVICE;
   }
-  rc = run_prep(d, in, workspace, !reuse, st);
-  if (rc) return rc;
-
   const Modes m = modes_of(d);
   SfmWsLayout L;
   sfm_ws_layout(d, &L);
@@ -225,6 +223,21 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   if (m.use_ssim) mode |= SFM_MODE_SSIM;
   if (grads) mode |= SFM_MODE_GRAD;
   if (dbg) mode |= SFM_MODE_DEBUG;
+  // prologue kernel: pyramid + tables + cell reset and, in the same grid, the second-order smoothness tasks (the
+  // edge-aware variant reads the pyramid and is launched by sfm_launch_fused after it)
+  SfmSmoothParams sm{};
+  int sm_mode = 0;
+  p.sm_part = nullptr;
+  p.n_sm_part = 0;
+  if (m.use_smooth && !p.edge_smooth) {
+    sfm_plan_smooth(p, sm);
+    sm.part = (float*)(ws + L.off_smpart);
+    sm_mode = grads ? 2 : 1;
+    p.sm_part = sm.part;
+    p.n_sm_part = sm.n_ctas;
+  }
+  rc = run_prep(d, in, workspace, !reuse, &sm, sm_mode, st);
+  if (rc) return rc;
   return sfm_launch_fused(p, mode, st);
 }
 
@@ -285,7 +298,7 @@ extern "C" int sfm_pyramid(const SfmDesc* desc, const float* tgt, const float* s
   p.acc = (double*)(ws + L.off_acc);
   p.n_acc = 0;
   p.counter = nullptr;
-  return sfm_launch_prep(p, (cudaStream_t)stream);
+  return sfm_launch_prep(p, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int sfm_pyramid_export(const SfmDesc* desc, const void* workspace, int scale, float* tgt_out,
@@ -320,7 +333,7 @@ extern "C" int sfm_build_tables(const SfmDesc* desc, const float* poses, const f
   p.proj_out = proj_out; p.kinv_out = kinv_out;
   p.acc = nullptr; p.n_acc = 0; p.counter = nullptr;
   p.raw_pose_hw = desc->raw_pose_hw; p.posevec_out = nullptr;
-  return sfm_launch_prep(p, (cudaStream_t)stream);
+  return sfm_launch_prep(p, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int sfm_ingest_u8(int B, int S, int H, int W, int n_scales, const uint8_t* frames, const float* K_in,

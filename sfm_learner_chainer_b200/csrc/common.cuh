@@ -40,6 +40,7 @@ struct SfmWsLayout {
   size_t off_acc;                  // double [4 + B*S*ns*12] loss sums (pixel, smooth, exp, ssim) + dL/dP per scale
   size_t off_counter;              // unsigned: spare
   size_t off_posevec;              // float  [B][S][6]   6-DoF vectors reduced from the raw `poseout` map (raw_pose_hw > 0)
+  size_t off_smpart;               // float  [tasks / 8] loss partials of the smoothness CTAs of the prologue kernel
   size_t acc_doubles;
   size_t total;
 };
@@ -51,6 +52,23 @@ struct SfmWsLayout {
 #endif
 
 static inline size_t sfm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Decomposition of the second-order smoothness term into warp tasks (strips of SFM_SMOOTH_IW interior columns x hseg
+// rows of every (snippet, scale)); shared by the launcher (smooth.cu) and the workspace layout (one loss-partial slot
+// per 8 tasks).  Segment height: enough warps to cover the chip a few times, few enough that the 4 halo rows stay cheap.
+#define SFM_SMOOTH_IW 28
+static inline int sfm_smooth_plan(int B, int ns, int H, int W, int* hseg_out) {
+  int hseg = 64;
+  long long n = 0;
+  for (;;) {
+    n = 0;
+    for (int s = 0; s < ns; ++s) n += (long long)B * (((W >> s) + SFM_SMOOTH_IW - 1) / SFM_SMOOTH_IW) * (((H >> s) + hseg - 1) / hseg);
+    if (n >= 148 * 4 * 8 || hseg <= 8) break;
+    hseg >>= 1;
+  }
+  if (hseg_out) *hseg_out = hseg;
+  return (int)n;
+}
 
 static inline void sfm_ws_layout(const SfmDesc* d, SfmWsLayout* L) {
   size_t off = 0;
@@ -75,6 +93,8 @@ static inline void sfm_ws_layout(const SfmDesc* d, SfmWsLayout* L) {
   off = sfm_align_up(off + 8, 256);
   L->off_posevec = off;
   off = sfm_align_up(off + (size_t)d->B * d->S * 6 * sizeof(float), 256);
+  L->off_smpart = off;
+  off = sfm_align_up(off + (size_t)((sfm_smooth_plan(d->B, d->n_scales, d->H, d->W, nullptr) + 7) / 8) * sizeof(float), 256);
   L->total = off;
 }
 

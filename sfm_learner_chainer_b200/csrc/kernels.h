@@ -24,12 +24,29 @@ struct SfmPrepParams {
   float* posevec_out;
   // filled by the launcher
   long long pix_begin[SFM_MAX_SCALES];
-  int n_pyr_blocks;
+  int n_pyr_blocks, n_tail_blocks;
+  int n_mix_region;  // the smoothness CTAs are spread evenly over the first n_mix_region blocks after the tail blocks
   int vec0;          // scale 0 copied 4 pixels per thread
   int band, split;   // full-resolution rows per pyramid CTA; warps sharing one row
 };
 
-int sfm_launch_prep(const SfmPrepParams& p, cudaStream_t stream);
+// Second-order smoothness tasks that ride in the prologue kernel (smooth_task.cuh): strips x row segments of every
+// (snippet, scale), one per warp of n_ctas 8-warp CTAs; CTA k writes its loss partial to part[k].
+struct SfmSmoothParams {
+  int ns, hseg, n_tasks, n_ctas;
+  int h[SFM_MAX_SCALES], w[SFM_MAX_SCALES];
+  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];
+  int tile_begin[SFM_MAX_SCALES + 1];
+  const float* disp[SFM_MAX_SCALES];
+  float* gdisp[SFM_MAX_SCALES];
+  float k_dx2[SFM_MAX_SCALES], k_mix[SFM_MAX_SCALES], k_dy2[SFM_MAX_SCALES];
+  const float* gy;
+  unsigned raw_disp_mask;
+  float* part;       // [n_ctas] loss partials (workspace)
+};
+
+// sm_mode: 0 = no smoothness tasks, 1 = loss only, 2 = loss + gdisp
+int sfm_launch_prep(const SfmPrepParams& p, const SfmSmoothParams* sm, int sm_mode, cudaStream_t stream);
 int sfm_launch_ingest_u8(int B, int S, int H, int W, int ns, const uint8_t* frames, const float* K_in, const SfmAugment* aug,
                          float* tgt, float* src, float* K_out, cudaStream_t stream);   // ingest.cu
 size_t sfm_eval_scratch_bytes_impl(int B, int Hg, int Wg);                                  // eval.cu
@@ -42,10 +59,6 @@ int sfm_launch_pose_reduce(int B, int S, int hw, const float* x, float* poses_ou
 struct SfmFusedParams {
   int B, S, ns;
   int h[SFM_MAX_SCALES], w[SFM_MAX_SCALES];
-  // strip decomposition of the smoothness kernel: tiles_x = strips, tiles_y = row segments of sm_hseg rows
-  int tiles_x[SFM_MAX_SCALES], tiles_y[SFM_MAX_SCALES];
-  int tile_begin[SFM_MAX_SCALES + 1];
-  int sm_hseg;
   // warp-task decomposition (marching kernels): a warp owns a 32-column strip x hseg rows of one (snippet, scale)
   int hseg;
   int nstrip[SFM_MAX_SCALES], nseg[SFM_MAX_SCALES];
@@ -68,6 +81,8 @@ struct SfmFusedParams {
   unsigned raw_disp_mask;   // bit s: disp[s] is pre-activation, gdisp[s] the gradient w.r.t. it
   const float* gy;          // upstream gradient (device scalar) or nullptr
   double* acc;              // [4 + B*S*12]
+  const float* sm_part;     // loss partials of the smoothness CTAs of the prologue kernel
+  int n_sm_part;
   unsigned* counter;
   float* losses_out;        // [5] or nullptr
   float* gposes;            // [B][S][6] or nullptr
@@ -112,7 +127,8 @@ static inline cudaError_t sfm_launch_kernel(K kernel, unsigned grid, unsigned bl
 // mode bits for the launcher
 enum { SFM_MODE_EXP = 1, SFM_MODE_SSIM = 2, SFM_MODE_GRAD = 4, SFM_MODE_DEBUG = 8 };
 int sfm_launch_fused(SfmFusedParams& p, int mode, cudaStream_t stream);
-int sfm_launch_smooth(SfmFusedParams& p, int grad, cudaStream_t stream);   // smooth.cu
+void sfm_plan_smooth(const SfmFusedParams& p, SfmSmoothParams& q);                 // smooth.cu
+int sfm_launch_edge_smooth(SfmFusedParams& p, int grad, cudaStream_t stream);      // smooth.cu
 extern thread_local cudaEvent_t sfm_ev_start, sfm_ev_stop;   // profiling hook (sfm_set_kernel_events)
 
 int sfm_launch_scale(float* const* ptrs, const long long* counts, int n, const float* gy, cudaStream_t stream);

@@ -1,11 +1,16 @@
 // prep.cu -- per-step prologue kernel: image pyramid (F.resize_images, base_model.py:70-72), scales >= 1 only and
 // planar like the caller's tensors (scale 0 is the identity and is never copied: the loss kernels read it from
 // the caller's tensors), the 3x4 projection tables (proj_tgt_to_src, transform.py:64-91) and inverse intrinsics
-// (F.batch_inv, transform.py:105), and the reset of the fp64 reduction cells the fused loss kernel accumulates into.
+// (F.batch_inv, transform.py:105), the reset of the fp64 reduction cells the fused loss kernel accumulates into --
+// and, in the same grid, the second-order smoothness tasks (smooth_task.cuh): they depend on the caller's disparity
+// alone and are issue-bound while the pyramid CTAs are memory-bound, so CTAs of both kinds are interleaved in one
+// launch and share the SMs (as separate dependent launches they ran almost back to back: a dependent grid is only
+// released when the last wave of its predecessor has started).
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "smooth_task.cuh"
 
 namespace {
 
@@ -28,12 +33,19 @@ struct PrepRow {
 // Coordinates follow Chainer's resize_images: u = linspace(0, W-1, w_s) in float64 (x*step, last
 // element pinned to W-1), u0 = clip(floor(u), 0, W-2), weights are float64 products cast to fp32,
 // y = ((w1*a + w2*b) + w3*c) + w4*d in fp32.
-__global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_constant__ SfmPrepParams p) {
-  const int blk = blockIdx.x;
-  cudaTriggerProgrammaticLaunchCompletion();      // the smoothness kernel may start once every CTA of this grid runs
-  if (blk >= p.n_pyr_blocks) {
-    // ---- tables + accumulator reset (a handful of trailing CTAs)
-    const int t = (blk - p.n_pyr_blocks) * kPrepThreads + threadIdx.x;
+// Block roles: [0, n_tail) tables + cell reset; then the n_pyr_blocks pyramid CTAs and the n_sm smoothness CTAs, the
+// latter spread evenly over the first R = n_mix_region blocks (block i < R is a smoothness CTA when
+// floor((i+1) n_sm / R) > floor(i n_sm / R)): the long, issue-bound smoothness CTAs start early and the short,
+// memory-bound pyramid CTAs fill the SMs around them and run on alone at the end.
+// SM: 0 = no smoothness tasks, 1 = loss only, 2 = loss and gdisp.  No early programmatic-launch trigger: the dependent
+// fused kernel's CTAs would pile up on whichever SMs are free first (measured, see the launch policy notes in DESIGN.md).
+template <int SM>
+__global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_constant__ SfmPrepParams p,
+                                                                const __grid_constant__ SfmSmoothParams sm) {
+  int blk = blockIdx.x;
+  if (blk < p.n_tail_blocks) {
+    // ---- tables + accumulator reset (a handful of leading CTAs)
+    const int t = blk * kPrepThreads + threadIdx.x;
     const int n_proj = p.build_tables ? p.B * p.S * p.ns : 0;
     const int n_kinv = p.build_tables ? p.B * p.ns : 0;
     if (t < n_proj) {
@@ -65,6 +77,31 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
       if (j == p.n_acc && p.counter) *p.counter = 0u;
     }
     return;
+  }
+
+  blk -= p.n_tail_blocks;
+  if (SM != 0) {
+    const long long R = p.n_mix_region;
+    const int k0 = (blk < R) ? (int)(((long long)blk * sm.n_ctas) / R) : sm.n_ctas;
+    const int k1 = (blk < R) ? (int)(((long long)(blk + 1) * sm.n_ctas) / R) : sm.n_ctas;
+    if (k1 > k0) {
+      // ---- smoothness CTA k0: one task per warp
+      __shared__ float s_part[kPrepThreads / 32];
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int t = k0 * (kPrepThreads / 32) + warp;
+      float loss = (t < sm.n_tasks) ? sfm_smooth_task<SM == 2>(sm, t, lane) : 0.f;
+      loss = sfm_warp_sum(loss);
+      if (lane == 0) s_part[warp] = loss;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPrepThreads / 32; ++k) tot += s_part[k];
+        sm.part[k0] = tot;
+      }
+      return;
+    }
+    blk -= k0;
   }
 
   // ---- pyramid
@@ -156,8 +193,10 @@ __global__ void sfm_pose_reduce_kernel(const float* __restrict__ x, float* __res
 
 }  // namespace
 
-int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
+int sfm_launch_prep(const SfmPrepParams& p_in, const SfmSmoothParams* sm_in, int sm_mode, cudaStream_t stream) {
   SfmPrepParams p = p_in;
+  SfmSmoothParams sm = sm_in ? *sm_in : SfmSmoothParams{};
+  if (!sm_in || sm.n_ctas <= 0) sm_mode = 0;
   // full-resolution rows per pyramid CTA: 8, or 4 / 2 while the grid would not fill the chip twice (small batches are
   // latency-bound here: a thread walks band/2 rows of scale 1, so shorter bands mean shorter walks)
   p.band = 8;
@@ -170,8 +209,20 @@ int sfm_launch_prep(const SfmPrepParams& p_in, cudaStream_t stream) {
   p.split = 1;
   p.n_pyr_blocks = (p.do_pyramid && p.ns > 1) ? p.B * (1 + p.S) * ((p.H + p.band - 1) / p.band) : 0;
   const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;
-  const int tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
-  sfm_prep_kernel<<<p.n_pyr_blocks + tail_blocks, kPrepThreads, 0, stream>>>(p);
+  p.n_tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
+  const unsigned grid = (unsigned)(p.n_tail_blocks + p.n_pyr_blocks + (sm_mode ? sm.n_ctas : 0));
+  {
+    int pct = 75;
+    const char* e = getenv("SFM_SM_FRAC");        // development knob: share of the grid over which the smoothness CTAs are spread
+    if (e && atoi(e) > 0 && atoi(e) <= 100) pct = atoi(e);
+    const long long n_mix = (long long)p.n_pyr_blocks + sm.n_ctas;
+    long long R = n_mix * pct / 100;
+    if (R < sm.n_ctas) R = sm.n_ctas;
+    p.n_mix_region = (int)R;
+  }
+  if (sm_mode == 2) sfm_prep_kernel<2><<<grid, kPrepThreads, 0, stream>>>(p, sm);
+  else if (sm_mode == 1) sfm_prep_kernel<1><<<grid, kPrepThreads, 0, stream>>>(p, sm);
+  else sfm_prep_kernel<0><<<grid, kPrepThreads, 0, stream>>>(p, sm);
   SFM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -102,9 +102,10 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
   const float wssim = gyv * p.ssim_rate * inv_n3;
   // SSIM on raw 3x3 window SUMS (9 x the means): the 1/81 factors of numerator and denominator cancel
   const float C1 = 81.f * (0.01f * 0.01f), C2 = 81.f * (0.03f * 0.03f);
-  cudaTriggerProgrammaticLaunchCompletion();           // lets the epilogue's CTAs become resident while this grid drains
-  // everything below reads what the prep kernel (pyramid, tables) and the smoothness kernel (gdisp) wrote
+  // everything below reads what the prologue kernel wrote (pyramid, tables, the smoothness tasks' gdisp)
   cudaGridDependencySynchronize();
+  cudaTriggerProgrammaticLaunchCompletion();           // lets the epilogue's CTAs become resident while this grid drains (after the
+                                                       // wait: the epilogue reads the prologue's smoothness partials ahead of its own wait)
   const float* __restrict__ kinvp = p.kinv + ((size_t)b * p.ns + s) * 9;
   const float xf = (float)xx;
   const bool raw = RAW && ((p.raw_disp_mask >> s) & 1u);    // RAW: some scale takes the pre-activation disparity map
