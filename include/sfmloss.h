@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SFM_VERSION 101           /* major*100 + minor */
+#define SFM_VERSION 102           /* major*100 + minor */
 #define SFM_MAX_SCALES 4          /* base_model.py:66 (len(pred_depthes) == 4) */
 #define SFM_MAX_SOURCES 8         /* seq_len-1; shipped configs use 2 and 4 */
 
@@ -38,6 +38,7 @@ extern "C" {
 #define SFM_E_NULL_POINTER (-3)
 #define SFM_E_UNSUPPORTED (-4)
 #define SFM_E_NO_DEVICE (-5)
+#define SFM_E_COMM (-6)           /* a collective failed (NCCL error in sfm_last_error) */
 
 /* SfmDesc.flags */
 #define SFM_FLAG_TABLES_PROVIDED 0x1u /* caller supplies proj/kinv tables (bit-exact tests; the reference
@@ -253,6 +254,27 @@ int sfm_loss_step_host_wait(SfmHostCtx* ctx);
  * The H2D copy carries 1 byte per image sample instead of 4.  Complete with sfm_loss_step_host_wait. */
 int sfm_loss_step_host_u8_submit(SfmHostCtx* ctx, const uint8_t* frames, const float* K_in, const SfmAugment* aug,
                                  const SfmInputs* in, float* losses_out, const SfmGrads* grads);
+
+/* ---- Multi-GPU: the path shards by snippet (SfmDesc.B_global), gradients need no communication, and the five loss
+ * partials are completed by ONE all-reduce (sum, float32) per step.  Replaces the reduce of Chainer's
+ * MultiprocessParallelUpdater (config_utils.py:123-126, unused by the shipped configs) for this path.
+ * One process per GPU.  The communicator wraps an NCCL communicator (bound at run time with dlopen, so the library
+ * loads without NCCL; sfm_nccl_set_library names the shared object when the process has not loaded one already):
+ *   rank 0:      sfm_comm_unique_id(id)            -> 128 opaque bytes, handed to the other ranks by the host program
+ *                                                     (MPI, torch.distributed, a file ...)
+ *   every rank:  sfm_comm_create(id, nranks, rank, &comm)     collective, on the rank's current device
+ *   every step:  sfm_allreduce_partials(comm, losses, 5, stream)   in place on the device array `losses`; enqueued on
+ *                                                     `stream` (after the loss call that wrote it), asynchronous,
+ *                                                     capturable in a CUDA graph together with the step
+ *   at the end:  sfm_comm_destroy(comm)                                                                          */
+#define SFM_NCCL_UNIQUE_ID_BYTES 128
+typedef struct SfmComm SfmComm;
+int sfm_nccl_set_library(const char* path);
+int sfm_nccl_version(void);                /* ncclGetVersion code (e.g. 22809), 0 when NCCL cannot be loaded */
+int sfm_comm_unique_id(void* id_out);
+int sfm_comm_create(const void* unique_id, int nranks, int rank, SfmComm** comm_out);
+int sfm_comm_destroy(SfmComm* comm);
+int sfm_allreduce_partials(SfmComm* comm, float* losses, int count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,14 @@ class SFMLearner(object):
         do_exp = self.exp_reg is not None and self.exp_reg > 0
         pred_poses, pred_maskes = self.pose_net(tgt_img, stacked_src_imgs, do_exp=do_exp)
         first = pred_disps[0]
-        if D.is_torch(first) and getattr(first, 'requires_grad', False):
+        needs_grad = D.is_torch(first) and any(getattr(t, 'requires_grad', False)
+                                               for t in list(pred_disps) + list(pred_poses if isinstance(pred_poses, (tuple, list)) else [pred_poses])
+                                               + list(pred_maskes or []))
+        if needs_grad:
+            import torch
+            if not torch.is_grad_enabled():
+                needs_grad = False
+        if needs_grad:
             from .torch_adapter import view_synthesis_loss
             total, losses = view_synthesis_loss(self.loss_op, tgt_img, src_imgs, intrinsics, pred_disps,
                                                 pred_poses, pred_maskes)
@@ -52,8 +59,21 @@ class SFMLearner(object):
             total, losses = view_synthesis_loss(self.loss_op, tgt_img, src_imgs, intrinsics, pred_disps,
                                                 pred_poses, pred_maskes)
         else:
+            # array-level call (also torch tensors under torch.no_grad(), e.g. validation): PoseNet returns a tuple of
+            # S (B, 6) vectors (pose_net.py:52-54); the operator takes one (B, S, 6) array
             if isinstance(pred_poses, (tuple, list)):
-                raise TypeError('array-level call needs pred_poses as one (B,S,6) device array')
+                if D.is_torch(first):
+                    import torch
+                    pred_poses = torch.stack([p.detach() for p in pred_poses], dim=1).contiguous()
+                elif D.is_cupy(first):
+                    import cupy
+                    pred_poses = cupy.ascontiguousarray(cupy.stack(list(pred_poses), axis=1))
+                else:
+                    raise TypeError('array-level call needs pred_poses as one (B,S,6) device array')
+            if D.is_torch(first):
+                pred_disps = [t.detach().contiguous() for t in pred_disps]
+                pred_maskes = [t.detach().contiguous() for t in pred_maskes] if pred_maskes is not None else None
+                pred_poses = pred_poses.detach()
             losses, self.last_grads = self.loss_op.forward_backward(tgt_img, src_imgs, intrinsics, pred_disps,
                                                                     pred_poses, pred_maskes)
             total = losses[0]

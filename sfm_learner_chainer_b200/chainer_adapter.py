@@ -32,10 +32,49 @@ def make_function_node_class(base):
             self._grads = None
 
         def check_type_forward(self, in_types):
-            pass                                  # shape/dtype checks happen in ViewSynthesisLoss._pack
+            # Same style as spational_transformer_sampler_interp.py:11-24 (type_check.expect on dtype kind, ndim and the
+            # shapes that tie the inputs together), so that a wrong net output fails here, before any device work.
+            ns, S = self.op.n_scales, int(self.src_imgs.shape[1])
+            n_in = ns + 1 + (ns if self.op.use_exp else 0)
+            if _HAVE_CHAINER:
+                from chainer.utils import type_check
+                type_check.expect(in_types.size() == n_in)
+                B = int(self.src_imgs.shape[0])
+                H, W = int(self.src_imgs.shape[3]), int(self.src_imgs.shape[4])
+                for s in range(ns):
+                    t = in_types[s]
+                    type_check.expect(t.dtype.kind == 'f', t.ndim == 4, t.shape[0] == B, t.shape[1] == 1,
+                                      t.shape[2] == (H >> s), t.shape[3] == (W >> s))
+                pt = in_types[ns]
+                type_check.expect(pt.dtype.kind == 'f', pt.ndim == 3, pt.shape[0] == B, pt.shape[1] == S, pt.shape[2] == 6)
+                if self.op.use_exp:
+                    for s in range(ns):
+                        t = in_types[ns + 1 + s]
+                        type_check.expect(t.dtype.kind == 'f', t.ndim == 4, t.shape[0] == B, t.shape[1] == S,
+                                          t.shape[2] == (H >> s), t.shape[3] == (W >> s))
+            else:
+                self._check_inputs_plain(in_types, n_in)
+
+        def _check_inputs_plain(self, inputs, n_in):
+            """The same conditions without chainer.utils.type_check (duck-typed bases in tests): raises TypeError."""
+            ns, S = self.op.n_scales, int(self.src_imgs.shape[1])
+            B, H, W = int(self.src_imgs.shape[0]), int(self.src_imgs.shape[3]), int(self.src_imgs.shape[4])
+            if len(inputs) != n_in:
+                raise TypeError('expected %d inputs (pred_disps, pred_poses%s), got %d' % (
+                    n_in, ', pred_maskes' if self.op.use_exp else '', len(inputs)))
+            want = [(B, 1, H >> s, W >> s) for s in range(ns)] + [(B, S, 6)]
+            if self.op.use_exp:
+                want += [(B, S, H >> s, W >> s) for s in range(ns)]
+            for k, (a, shp) in enumerate(zip(inputs, want)):
+                if 'float32' not in str(a.dtype):
+                    raise TypeError('input %d: expected dtype float32, got %s' % (k, a.dtype))
+                if tuple(a.shape) != shp:
+                    raise TypeError('input %d: expected shape %s, got %s' % (k, shp, tuple(a.shape)))
 
         def forward(self, inputs):
             ns = self.op.n_scales
+            if not _HAVE_CHAINER:                  # chainer's FunctionNode.apply runs check_type_forward itself
+                self._check_inputs_plain(inputs, ns + 1 + (ns if self.op.use_exp else 0))
             disps, poses = list(inputs[:ns]), inputs[ns]
             logits = list(inputs[ns + 1:]) if self.op.use_exp else None
             self.losses, self._grads = self.op.forward_backward(self.tgt_img, self.src_imgs, self.intrinsics,

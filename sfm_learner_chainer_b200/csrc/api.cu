@@ -477,12 +477,23 @@ extern "C" int sfm_loss_step_host_u8_submit(SfmHostCtx* c, const uint8_t* frames
   if (!c || !frames || !K_in || !in) { sfm_set_error("sfm_loss_step_host_u8_submit: null pointer"); return SFM_E_NULL_POINTER; }
   const SfmDesc* d = &c->desc;
   const size_t n_frames = (size_t)d->B * (1 + d->S) * d->H * d->W * 3;
-  if (!c->d_frames) {
-    int rc;
-    if ((rc = host_alloc(c, (void**)&c->d_frames, n_frames))) return rc;
-    if ((rc = host_alloc(c, (void**)&c->d_aug, (size_t)d->B * sizeof(SfmAugment)))) return rc;
-    if ((rc = host_alloc(c, (void**)&c->d_Kin, (size_t)d->B * 9 * sizeof(float)))) return rc;
+  if (aug) {
+    // the crop window must lie inside the rescaled image (kitti_raw_transformed.py:36-50); the kernel trusts these
+    for (int b = 0; b < d->B; ++b) {
+      const SfmAugment& a = aug[b];
+      if (a.out_h < d->H || a.out_w < d->W || a.off_y < 0 || a.off_x < 0 || a.off_y > a.out_h - d->H || a.off_x > a.out_w - d->W ||
+          !(a.x_scaling > 0.0) || !(a.y_scaling > 0.0)) {
+        sfm_set_error("sfm_loss_step_host_u8_submit: aug[%d] is invalid (out %dx%d, offset %d,%d for a %dx%d crop)", b, a.out_h, a.out_w,
+                      a.off_y, a.off_x, d->H, d->W);
+        return SFM_E_INVALID_DESC;
+      }
+    }
   }
+  // each buffer is guarded on its own: a failed allocation leaves the others usable and is retried by the next call
+  int rc0;
+  if (!c->d_frames && (rc0 = host_alloc(c, (void**)&c->d_frames, n_frames))) return rc0;
+  if (!c->d_aug && (rc0 = host_alloc(c, (void**)&c->d_aug, (size_t)d->B * sizeof(SfmAugment)))) return rc0;
+  if (!c->d_Kin && (rc0 = host_alloc(c, (void**)&c->d_Kin, (size_t)d->B * 9 * sizeof(float)))) return rc0;
   cudaStream_t st = c->stream;
   SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_frames, frames, n_frames, cudaMemcpyHostToDevice, st));
   SFM_CUDA_CHECK(cudaMemcpyAsync(c->d_Kin, K_in, (size_t)d->B * 9 * sizeof(float), cudaMemcpyHostToDevice, st));

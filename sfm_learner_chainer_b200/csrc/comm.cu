@@ -1,0 +1,135 @@
+// comm.cu -- the one collective of the sharded path: the all-reduce of the five loss partials (SURVEY 8(e);
+// the reference analogue is Chainer's MultiprocessParallelUpdater reduce, config_utils.py:123-126).
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy the process already holds, e.g. the one bundled
+// with torch, or the one named with sfm_nccl_set_library) so that libsfmloss.so itself has no link-time NCCL
+// dependency and still loads on a machine without it.  Only the five entry points below are used, with the
+// enum values of nccl.h 2.x (ncclFloat = 7, ncclSum = 0, ncclUniqueId = 128 opaque bytes).
+// The all-reduce is enqueued on the caller's stream and is capturable in a CUDA graph, so the per-step call
+// costs no host work when the step is replayed as a graph.
+#include <dlfcn.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[SFM_NCCL_UNIQUE_ID_BYTES]; } ncclUniqueId;
+typedef int ncclResult_t;
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+std::string g_nccl_path;
+
+int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.handle) return 0;
+  void* h = nullptr;
+  if (!g_nccl_path.empty()) h = dlopen(g_nccl_path.c_str(), RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy this process already mapped (torch's)
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    sfm_set_error("NCCL is not available: %s (name the library with sfm_nccl_set_library)", dlerror());
+    return SFM_E_UNSUPPORTED;
+  }
+  NcclApi a;
+  a.handle = h;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+  a.GetVersion = (decltype(a.GetVersion))dlsym(h, "ncclGetVersion");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString) {
+    sfm_set_error("libnccl is missing one of ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy / ncclAllReduce");
+    return SFM_E_UNSUPPORTED;
+  }
+  g_nccl = a;
+  return 0;
+}
+
+int nccl_check(ncclResult_t r, const char* what) {
+  if (r == 0) return 0;
+  sfm_set_error("%s failed: NCCL error %d (%s)", what, (int)r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return SFM_E_COMM;
+}
+
+}  // namespace
+
+struct SfmComm {
+  ncclComm_t comm;
+  int nranks, rank;
+};
+
+extern "C" int sfm_nccl_set_library(const char* path) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.handle) { sfm_set_error("sfm_nccl_set_library: NCCL is already loaded"); return SFM_E_UNSUPPORTED; }
+  g_nccl_path = path ? path : "";
+  return 0;
+}
+
+extern "C" int sfm_nccl_version(void) {
+  if (nccl_load()) return 0;
+  int v = 0;
+  if (g_nccl.GetVersion && g_nccl.GetVersion(&v) == 0) return v;
+  return 0;
+}
+
+extern "C" int sfm_comm_unique_id(void* id_out) {
+  if (!id_out) { sfm_set_error("sfm_comm_unique_id: id_out is NULL"); return SFM_E_NULL_POINTER; }
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId id;
+  if ((rc = nccl_check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId"))) return rc;
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int sfm_comm_create(const void* unique_id, int nranks, int rank, SfmComm** comm_out) {
+  if (!unique_id || !comm_out) { sfm_set_error("sfm_comm_create: null pointer"); return SFM_E_NULL_POINTER; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { sfm_set_error("sfm_comm_create: rank %d outside a world of %d", rank, nranks); return SFM_E_INVALID_DESC; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { sfm_set_error("no CUDA device: libsfmloss has no CPU fallback"); return SFM_E_NO_DEVICE; }
+  int rc = nccl_load();
+  if (rc) return rc;
+  SfmComm* c = new (std::nothrow) SfmComm();
+  if (!c) { sfm_set_error("out of host memory"); return SFM_E_INVALID_DESC; }
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  c->nranks = nranks;
+  c->rank = rank;
+  if ((rc = nccl_check(g_nccl.CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank"))) { delete c; return rc; }
+  *comm_out = c;
+  return 0;
+}
+
+extern "C" int sfm_comm_destroy(SfmComm* comm) {
+  if (!comm) return 0;
+  int rc = 0;
+  if (g_nccl.CommDestroy) rc = nccl_check(g_nccl.CommDestroy(comm->comm), "ncclCommDestroy");
+  delete comm;
+  return rc;
+}
+
+extern "C" int sfm_allreduce_partials(SfmComm* comm, float* losses, int count, void* stream) {
+  if (!comm || !losses) { sfm_set_error("sfm_allreduce_partials: null pointer"); return SFM_E_NULL_POINTER; }
+  if (count < 1) { sfm_set_error("sfm_allreduce_partials: count %d < 1", count); return SFM_E_INVALID_SHAPE; }
+  return nccl_check(g_nccl.AllReduce(losses, losses, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, comm->comm, (cudaStream_t)stream),
+                    "ncclAllReduce");
+}

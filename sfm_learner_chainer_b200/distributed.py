@@ -40,6 +40,61 @@ def allreduce_loss_partials(losses, group=None, async_op=False):
     return dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class LossPartialsComm(object):
+    """The C-ABI communicator of the path's one collective (include/sfmloss.h: sfm_comm_* / sfm_allreduce_partials):
+    an NCCL communicator owned by libsfmloss, one process per GPU.  The 128-byte NCCL id is produced on rank 0 and
+    handed to the other ranks through `exchange`, a callable (bytes-or-None) -> bytes that broadcasts rank 0's
+    value; the default uses the initialised torch.distributed process group (any backend).
+
+        comm = LossPartialsComm(rank, world)            # collective: every rank calls it, on its own device
+        comm.allreduce(losses_dev, stream)              # in place, asynchronous on `stream`, graph-capturable
+    """
+
+    def __init__(self, rank, world_size, exchange=None, nccl_library=None):
+        import ctypes as C
+        from . import lib as L
+        self._L, self._lib = L, L.load()
+        self.rank, self.world_size = int(rank), int(world_size)
+        if nccl_library:
+            L.check(self._lib.sfm_nccl_set_library(str(nccl_library).encode()))
+        buf = (C.c_char * L.SFM_NCCL_UNIQUE_ID_BYTES)()
+        if self.rank == 0:
+            L.check(self._lib.sfm_comm_unique_id(C.cast(buf, C.c_void_p)))
+        ident = (exchange or self._torch_exchange)(bytes(buf.raw) if self.rank == 0 else None)
+        if len(ident) != L.SFM_NCCL_UNIQUE_ID_BYTES:
+            raise ValueError('exchange() must return the %d bytes of rank 0' % L.SFM_NCCL_UNIQUE_ID_BYTES)
+        ibuf = (C.c_char * L.SFM_NCCL_UNIQUE_ID_BYTES).from_buffer_copy(ident)
+        self._comm = C.c_void_p()
+        L.check(self._lib.sfm_comm_create(C.cast(ibuf, C.c_void_p), self.world_size, self.rank, C.byref(self._comm)))
+
+    @staticmethod
+    def _torch_exchange(ident):
+        import torch.distributed as dist
+        box = [ident]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def allreduce(self, losses, stream=None, count=5):
+        """Sums the first `count` floats of the device array `losses` over the ranks, in place, on `stream` (an integer
+        cudaStream_t; default: the array's current stream)."""
+        import ctypes as C
+        from . import device as D
+        D.check_array(losses, 'losses')
+        st = D.current_stream(losses) if stream is None else stream
+        self._L.check(self._lib.sfm_allreduce_partials(self._comm, C.c_void_p(D.ptr(losses)), int(count), C.c_void_p(st)))
+
+    def close(self):
+        if getattr(self, '_comm', None):
+            self._lib.sfm_comm_destroy(self._comm)
+            self._comm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:            # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
 class ShardedViewSynthesisLoss(object):
     """ViewSynthesisLoss over this rank's snippet shard; losses are completed by an allreduce.
 
@@ -48,9 +103,10 @@ class ShardedViewSynthesisLoss(object):
     the true global batch.  Every other ViewSynthesisLoss keyword (raw_disp_scales, raw_pose, edge_aware_smooth,
     n_scales) is forwarded."""
 
-    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None, **kwargs):
+    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None, comm=None, **kwargs):
         from .functions import ViewSynthesisLoss
         self.group = group
+        self.comm = comm                            # LossPartialsComm: the all-reduce then runs through the C ABI, on the loss call's stream
         self.op = ViewSynthesisLoss(smooth_reg, exp_reg, ssim_rate, B_global=B_global, **kwargs)
         self._explicit = B_global is not None
         self._b_local = None                        # local batch the cached sum was taken for
@@ -79,5 +135,8 @@ class ShardedViewSynthesisLoss(object):
     def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, async_op=False, **kwargs):
         self._resolve_global_batch(src)
         losses, grads = self.op.forward_backward(tgt, src, intrinsics, disps, poses, logits, **kwargs)
+        if self.comm is not None:
+            self.comm.allreduce(losses)
+            return losses, grads, None
         work = allreduce_loss_partials(losses, self.group, async_op=async_op)
         return losses, grads, work

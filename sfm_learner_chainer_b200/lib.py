@@ -18,6 +18,8 @@ SFM_E_INVALID_SHAPE = -2
 SFM_E_NULL_POINTER = -3
 SFM_E_UNSUPPORTED = -4
 SFM_E_NO_DEVICE = -5
+SFM_E_COMM = -6
+SFM_NCCL_UNIQUE_ID_BYTES = 128
 
 LOSS_KEYS = ('total_loss', 'pixel_loss', 'smooth_loss', 'exp_loss', 'ssim_loss')   # base_model.py:119-123
 
@@ -81,6 +83,12 @@ SYMBOLS = {
     'sfm_loss_step_host_submit': (_i, [_vp, _I, _vp, _G]),
     'sfm_loss_step_host_wait': (_i, [_vp]),
     'sfm_loss_step_host_u8_submit': (_i, [_vp, _vp, _vp, _vp, _I, _vp, _G]),
+    'sfm_nccl_set_library': (_i, [C.c_char_p]),
+    'sfm_nccl_version': (_i, []),
+    'sfm_comm_unique_id': (_i, [_vp]),
+    'sfm_comm_create': (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    'sfm_comm_destroy': (_i, [_vp]),
+    'sfm_allreduce_partials': (_i, [_vp, _vp, _i, _vp]),
 }
 
 _lib = None

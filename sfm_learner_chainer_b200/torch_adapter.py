@@ -19,11 +19,19 @@ class _ViewSynthesisLossFn(torch.autograd.Function):
                                             [l.detach() for l in logits] if logits else None)
         ctx.op, ctx.grads, ctx.shape = op, grads, tuple(src.shape)
         ctx.n_scales, ctx.use_exp = n_scales, use_exp
+        ctx.consumed = False
         ctx.mark_non_differentiable(losses)
         return losses[0].clone(), losses
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gy, _g_losses):
+        # The gradients were produced by the forward's fused pass and are rescaled IN PLACE by the upstream gradient;
+        # a second backward through the same node (retain_graph=True) would rescale them again, so it is refused.
+        if ctx.consumed:
+            raise RuntimeError('view_synthesis_loss: backward through the same loss node twice is not supported '
+                               '(its gradients are computed in the forward pass and rescaled in place); call the loss again')
+        ctx.consumed = True
         B, S, _, H, W = ctx.shape
         g = ctx.grads
         gy = gy.to(torch.float32).reshape(1).contiguous()

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(lib):
     so = lib.load()
     for name in declared:
         assert getattr(so, name) is not None
-    assert so.sfm_version() == 101
+    assert so.sfm_version() == 102
 
 
 def test_struct_layout_matches_header(lib):
@@ -61,6 +61,24 @@ def test_workspace_and_validation(lib):
     assert so.sfm_sampler_interp_forward(1, 3, 8, 8, 0, 4, None, None, None, None) == lib.SFM_E_INVALID_SHAPE
     with pytest.raises(lib.SfmError):
         lib.check(so.sfm_warp_backward(1, 8, 8, None, None, None, None, None, None, None, None, None, None))
+
+
+def test_comm_entry_points_without_a_device(lib):
+    """sfm_comm_* / sfm_allreduce_partials (SURVEY 8(b)): argument errors and the no-device error come back as codes;
+    NCCL itself is bound at run time (the copy torch ships is found here)."""
+    import torch  # noqa: F401  -- maps torch's bundled libnccl.so.2 into the process
+    so = lib.load()
+    assert so.sfm_comm_unique_id(None) == lib.SFM_E_NULL_POINTER
+    assert so.sfm_allreduce_partials(None, None, 5, None) == lib.SFM_E_NULL_POINTER
+    ident = C.create_string_buffer(lib.SFM_NCCL_UNIQUE_ID_BYTES)
+    comm = C.c_void_p()
+    assert so.sfm_comm_create(C.cast(ident, C.c_void_p), 2, 2, C.byref(comm)) == lib.SFM_E_INVALID_DESC
+    if not torch.cuda.is_available():
+        assert so.sfm_comm_create(C.cast(ident, C.c_void_p), 1, 0, C.byref(comm)) == lib.SFM_E_NO_DEVICE
+        assert b'no CPU fallback' in so.sfm_last_error()
+    v = so.sfm_nccl_version()
+    assert v == 0 or v >= 21000, v
+    assert so.sfm_comm_destroy(None) == 0
 
 
 def test_no_cpu_fallback(lib):

@@ -32,9 +32,29 @@ def _worker(rank, world, port, out_dir, B):
                                               [dev(x) for x in mine['disps']], dev(mine['poses']), None, async_op=True)
     work.wait()
     torch.cuda.synchronize()
+    # the same through the C ABI's own communicator (sfm_comm_* / sfm_allreduce_partials), captured in a CUDA graph
+    # together with the step: uneven shards, B_global left to the operator (sum of the local batches)
+    from sfm_learner_chainer_b200.distributed import LossPartialsComm
+    comm = LossPartialsComm(rank, world)
+    op2 = ShardedViewSynthesisLoss(comm=comm, **FLAGS)
+    args = (dev(mine['tgt']), dev(mine['src']), dev(mine['intrinsics']), [dev(x) for x in mine['disps']], dev(mine['poses']), None)
+    l2, g2, _ = op2.forward_backward(*args)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        l3, g3, _ = op2.forward_backward(*args)            # warm-up on the capture stream
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            l3, g3, _ = op2.forward_backward(*args)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
     lo, hi = shard_range(B, rank, world)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), losses=losses.cpu().numpy(), gposes=grads['gposes'].cpu().numpy(),
-             gdisp0=grads['gdisps'][0].cpu().numpy(), lo=lo, hi=hi)
+             gdisp0=grads['gdisps'][0].cpu().numpy(), lo=lo, hi=hi, losses_abi=l2.cpu().numpy(), losses_graph=l3.cpu().numpy(),
+             gdisp0_abi=g2['gdisps'][0].cpu().numpy(), B_global=op2.op.B_global)
+    comm.close()
     dist.destroy_process_group()
 
 
@@ -46,7 +66,7 @@ def test_sharded_result_equals_single_gpu_result(tmp_path):
     from sfm_learner_chainer_b200 import ViewSynthesisLoss
     from sfm_learner_chainer_b200.synthetic import make_snippets
     from tests.gpu_util import dev_inputs, host, assert_grad_close
-    world, B = 2, 6
+    world, B = 2, 5                                   # uneven shards: 3 + 2
     port = 29600 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, str(tmp_path), B), nprocs=world, join=True)
     d = make_snippets(B, 2, 128, 416, seed=90)
@@ -58,3 +78,7 @@ def test_sharded_result_equals_single_gpu_result(tmp_path):
         np.testing.assert_allclose(z['losses'][:5], host(lf)[:5], rtol=2e-6)            # every rank holds the full-batch losses
         np.testing.assert_array_equal(z['gdisp0'], host(gf['gdisps'][0])[sl])            # shard gradients are final, bit for bit
         assert_grad_close(z['gposes'], host(gf['gposes'])[sl], what='gposes of rank %d' % r)
+        assert int(z['B_global']) == B
+        np.testing.assert_allclose(z['losses_abi'][:5], host(lf)[:5], rtol=2e-6)         # C-ABI communicator, direct call
+        np.testing.assert_allclose(z['losses_graph'][:5], host(lf)[:5], rtol=2e-6)       # ... and replayed inside a CUDA graph
+        np.testing.assert_array_equal(z['gdisp0_abi'], host(gf['gdisps'][0])[sl])

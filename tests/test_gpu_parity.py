@@ -619,3 +619,32 @@ def test_back_to_back_calls_are_ordered(flagset):
         for s in range(4):
             np.testing.assert_array_equal(host(gr['gdisps'][s]), rg[s])
         np.testing.assert_allclose(host(gr['gposes']), rp, rtol=1e-5, atol=1e-9)
+
+
+def test_abi_communicator_world_of_one_inside_a_cuda_graph():
+    """sfm_comm_* / sfm_allreduce_partials on one GPU: a world of one leaves the partials unchanged, and the call is
+    capturable in a CUDA graph together with the step (the N-GPU equality is tests/test_gpu_multi.py)."""
+    import torch
+    from sfm_learner_chainer_b200.distributed import LossPartialsComm, ShardedViewSynthesisLoss
+    flags = FLAGSETS['v1_odom']
+    d = make_snippets(2, 2, 64, 208, seed=91)
+    g = dev_inputs(d)
+    ref, _ = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    comm = LossPartialsComm(0, 1, exchange=lambda ident: ident)
+    op = ShardedViewSynthesisLoss(comm=comm, **flags)
+    args = (g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    l1, _, _ = op.forward_backward(*args)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(l1), host(ref))
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        op.forward_backward(*args)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            l2, _, _ = op.forward_backward(*args)
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(l2), host(ref))
+    comm.close()
