@@ -4,18 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path (image pyramid + fused loss forward+backward, single sweep)
-over one batch of synthetic KITTI-shaped snippets.  Default workload = BASELINE.json configs[1]
-(sfm_learner_v1_ssim.yml loss path: SSIM + L1 + smoothness, B=4, S=2, 128x416, 4 scales) per GPU;
-under N GPUs the batch is sharded by snippet (weak scaling: 4 snippets per rank, B_global = 4N), the
-only exchange being the 5-float loss-partial allreduce (asynchronous, NCCL).
+One "step" = one pass of the hot path (pyramid / tables / smoothness prologue + fused loss forward+backward + epilogue,
+single sweep) over one batch of synthetic KITTI-shaped snippets.  Default workload = BASELINE.json configs[1]
+(sfm_learner_v1_ssim.yml loss path: SSIM + L1 + smoothness, B=4, S=2, 128x416, 4 scales) per GPU; under N GPUs the
+batch is sharded by snippet (weak scaling for `value`: 4 snippets per rank, B_global = 4N) and the path's one
+collective -- the 5-float loss-partial all-reduce, sfm_allreduce_partials of the C ABI -- runs EVERY step inside the
+timed CUDA-event interval (captured in the step's CUDA graph).
 
 Prints ONE JSON line (rank 0).  Keys beyond the driver's contract:
-  roofline       dominant kernel (fused loss) vs the measured HBM copy peak, timed live with CUDA events
-  roofline_step  whole step vs the strict byte model (SURVEY 8(d) "A-strict")
-  cpu_baseline   the numpy oracle (port of the reference's numpy/Chainer CPU path) on this box's cores
-  e2e            same metric through the C-ABI host-buffer entry point (H2D + kernels + D2H per step)
-  other_configs  device-timed numbers for the remaining single-GPU BASELINE shapes (cfg1, cfg4, cfg5)
+  roofline        dominant kernel (fused loss): SURVEY 8(d) A-strict bytes / its own duration (CUDA events recorded by
+                  the library around that launch) vs the measured HBM copy peak; the pyramid-as-input byte model and
+                  the ncu DRAM traffic of the same kernel ride along as extra keys
+  roofline_step   whole step vs A-strict
+  cpu_baseline    the numpy oracle (port of the reference's numpy/Chainer CPU path) on this box's cores
+  e2e             same metric through the C-ABI host-buffer entry point (H2D + kernels + D2H every step)
+  other_configs   device-timed numbers for the remaining single-GPU BASELINE shapes (cfg1, cfg4, cfg5)
+  strong_scaling  (N > 1) the split the north star names: cfg4 with a GLOBAL batch of 32 (32/N snippets per GPU) and, at
+                  N = 8, cfg5 with a global batch of 64, each without a collective, with the per-step loss all-reduce,
+                  and with a 159.5 MB stand-in CNN-gradient all-reduce running next to it
 """
 import argparse
 import ctypes as C
@@ -93,6 +99,18 @@ def cpu_oracle_run(cfg_name, n_iters, threads):
     return float(sec), threads, (B, S, H, W)
 
 
+def config_dict(cfg_name, world):
+    """The `config` object of the JSON line -- identical in the B200 arm and the reference arm (same workload)."""
+    c = CONFIGS[cfg_name]
+    pix = c['B'] * pyramid_pixels(c['H'], c['W'])
+    return dict(workload='%s: %s' % (cfg_name, describe(cfg_name)), per_gpu_batch=c['B'], global_batch=c['B'] * world,
+                sources=c['S'], H=c['H'], W=c['W'], n_scales=4,
+                units='target-pyramid pixels = B * sum_s h_s*w_s (%d per step per GPU)' % pix,
+                l2_policy='inputs and outputs rotated over ceil(2 x L2 / A-strict) + 1 buffer sets (more than twice the L2 '
+                          'capacity in total), so consecutive steps never find their inputs in L2',
+                snippets='4 distinct seeded snippets, tiled to the batch size (separate buffers per tile)')
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -107,9 +125,9 @@ def run_reference(args):
     line = dict(impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=max(1, args.steps),
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic',
-                config=dict(workload='%s: %s' % (args.config, describe(args.config)), B=B, S=S, H=H, W=W,
-                            note='numpy restatement (oracle/) of the reference numpy/Chainer CPU path; '
-                                 'chainer==4.0.0b1 is not installable in this image'),
+                config=config_dict(args.config, max(1, int(os.environ.get('WORLD_SIZE', args.gpus)))),
+                note='numpy restatement (oracle/) of the reference numpy/Chainer CPU path on the host cores; '
+                     'chainer==4.0.0b1 is not installable in this image.  Rank 0 alone runs it (one batch of the per-GPU size)',
                 cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind='port', sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -268,69 +286,6 @@ class Workload(object):
             self.graphs.append(g)
         torch.cuda.synchronize()
 
-    def time_pipelined(self, steps, warmup):
-        """Throughput with the image pyramid of batch k+1 built on a side stream while the loss kernels of batch k
-        run.  The pyramid (sfm_pyramid) depends on the input images alone -- in a training step it can be issued
-        as soon as the batch is on the device, long before the CNN outputs exist -- so the dependent part of the
-        path is sfm_loss_forward_backward with SFM_FLAG_REUSE_PYRAMID (tables, smoothness, fused loss, epilogue).
-        Every step still does all of its work inside the timed region.  Returns ms per step."""
-        torch, L = self.torch, self.L
-        desc_r = L.SfmDesc(self.desc.B, self.desc.S, self.desc.H, self.desc.W, 4, self.desc.B_global, self.desc.smooth_reg,
-                           self.desc.exp_reg, self.desc.ssim_rate, L.SFM_FLAG_REUSE_PYRAMID)
-        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
-
-        def pyr(k, stream):
-            t = self.sets[k]
-            L.check(self.lib.sfm_pyramid(C.byref(self.desc), C.c_void_p(t['tgt'].data_ptr()), C.c_void_p(t['src'].data_ptr()),
-                                         t['wsp'], C.c_void_p(stream)))
-
-        def loss(k, stream):
-            t = self.sets[k]
-            L.check(self.lib.sfm_loss_forward_backward(C.byref(desc_r), C.byref(t['inp']), C.c_void_p(t['losses'].data_ptr()),
-                                                       C.byref(t['g']), t['wsp'], C.c_void_p(stream)))
-        torch.cuda.synchronize()
-        with torch.cuda.stream(sa):
-            for k in range(self.nsets):
-                pyr(k, sa.cuda_stream)
-                loss(k, sa.cuda_stream)
-        torch.cuda.synchronize()
-        gp, gl = [], []
-        for k in range(self.nsets):
-            a, b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(a, stream=sb):
-                pyr(k, torch.cuda.current_stream().cuda_stream)
-            with torch.cuda.graph(b, stream=sa):
-                loss(k, torch.cuda.current_stream().cuda_stream)
-            gp.append(a)
-            gl.append(b)
-        torch.cuda.synchronize()
-        ev_p = [torch.cuda.Event() for _ in range(self.nsets)]
-        ev_l = [torch.cuda.Event() for _ in range(self.nsets)]
-        used = [False] * self.nsets
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(sb):
-            gp[0].replay()
-            ev_p[0].record(sb)
-        for k in range(warmup + steps):
-            j, jn = k % self.nsets, (k + 1) % self.nsets
-            if k == warmup:
-                sa.synchronize()
-                sb.synchronize()
-                e0.record(sa)
-            with torch.cuda.stream(sb):                       # pyramid of the next batch
-                if used[jn]:
-                    sb.wait_event(ev_l[jn])                   # its workspace is free again
-                gp[jn].replay()
-                ev_p[jn].record(sb)
-            with torch.cuda.stream(sa):                       # loss of this batch
-                sa.wait_event(ev_p[j])
-                gl[j].replay()
-                ev_l[j].record(sa)
-                used[j] = True
-        e1.record(sa)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps
-
     def step(self, k):
         if self.graphs is not None:
             self.graphs[k % self.nsets].replay()
@@ -378,18 +333,25 @@ class Workload(object):
         return float(np.mean(ts)), float(ts[len(ts) // 2])
 
 
-def run_e2e(cfg_name, steps, device, n_ctx=3, u8=False):
-    """Same metric through the host-buffer C-ABI entry point: pinned host inputs -> H2D -> pyramid + fused
-    fwd+bwd -> D2H of the five losses and every gradient, EVERY step.  `n_ctx` host contexts are used alternately
+def run_e2e(cfg_name, device, n_ctx=3, u8=False, min_steps=200, min_seconds=0.5, repeats=3):
+    """Same metric through the host-buffer C-ABI entry point: pinned host inputs -> H2D -> prologue + fused fwd+bwd ->
+    D2H of the five losses and every gradient, EVERY step.  `n_ctx` host contexts are used alternately
     (sfm_loss_step_host_submit / _wait), the way a data loader keeps the next step's copies in flight while the
-    current one computes; n_ctx=1 is the fully synchronous call.  Returns (Mpix/s, h2d bytes, d2h bytes, loss)."""
+    current one computes; n_ctx=1 is the fully synchronous call.  u8: the step is fed by decoded uint8 frames
+    (sfm_loss_step_host_u8_submit; the reference's real data layer, datasets/kitti/kitti_raw_dataset.py:12-14).
+    Each repeat runs at least `min_steps` steps and `min_seconds` of wall time whatever --steps says; the MEDIAN of
+    `repeats` repeats is returned.  -> dict(value Mpix/s, h2d, d2h, steps, h2d_gbs, repeats=[...])."""
     import torch
     from sfm_learner_chainer_b200 import lib as L
     lib = L.load()
     c = dict(CONFIGS[cfg_name])
     B, S, H, W = c.pop('B'), c.pop('S'), c.pop('H'), c.pop('W')
     exp = c['exp_reg'] != 0
-    d = make_snippets(B, S, H, W, seed=1)
+    d = make_snippets(min(B, 4), S, H, W, seed=1)
+    if B > 4:
+        rep = lambda a: np.ascontiguousarray(np.concatenate([a] * (B // 4) + [a[:B % 4]], 0))
+        d = dict(tgt=rep(d['tgt']), src=rep(d['src']), intrinsics=rep(d['intrinsics']), disps=[rep(x) for x in d['disps']],
+                 poses=rep(d['poses']), logits=[rep(x) for x in d['logits']])
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hin = dict(tgt=pin(d['tgt']), src=pin(d['src']), K=pin(d['intrinsics']), poses=pin(d['poses']),
                disps=[pin(x) for x in d['disps']], logits=[pin(x) for x in d['logits']])
@@ -449,107 +411,353 @@ def run_e2e(cfg_name, steps, device, n_ctx=3, u8=False):
                 L.check(lib.sfm_loss_step_host_wait(ctxs[j]))
         run(3 * n_ctx)
         torch.cuda.synchronize()
+        # size a repeat: at least min_steps steps and min_seconds of wall time
         t0 = time.perf_counter()
-        run(steps)
-        sec = (time.perf_counter() - t0) / steps
+        run(20)
+        per = (time.perf_counter() - t0) / 20
+        steps = int(max(min_steps, math.ceil(min_seconds / max(per, 1e-7))))
+        secs = []
+        for _ in range(repeats):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run(steps)
+            secs.append((time.perf_counter() - t0) / steps)
         loss = float(outs[(steps - 1) % n_ctx]['losses'][0])
     finally:
         for ctx in ctxs:
             lib.sfm_host_ctx_destroy(ctx)
-    return B * pyramid_pixels(H, W) / sec / 1e6, h2d, d2h, loss
+    pix = B * pyramid_pixels(H, W)
+    med = float(np.median(secs))
+    return dict(value=pix / med / 1e6, h2d=h2d, d2h=d2h, steps=steps, h2d_gbs=h2d / med / 1e9, loss=loss,
+                repeats=[pix / t / 1e6 for t in secs])
+
+
+def csrc_sha():
+    """Short hash of the kernel sources: profiles/ncu_latest.json records the one it was captured with, so a stale
+    capture is not quoted as the traffic of the kernels that run now."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'sfm_learner_chainer_b200', 'csrc')
+    for f in sorted(os.listdir(d)):
+        if f.endswith(('.cu', '.cuh', '.h')):
+            h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()[:16]
+
+
+def fused_kernel_name(c):
+    return 'sfm_ssim_march_kernel' if (c['ssim_rate'] and not c['exp_reg']) else 'sfm_l1_march_kernel'
+
+
+def ncu_traffic(cfg_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from the committed ncu --set full capture
+    of THIS source state (tools/ncu_to_json.py), else (None, why)."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_latest.json')))
+    except Exception as e:                                            # noqa: BLE001
+        return None, None, 'profiles/ncu_latest.json unreadable: %r' % (e,)
+    ent = prof.get(cfg_name)
+    if not ent:
+        return None, None, 'no capture of %s in profiles/ncu_latest.json' % cfg_name
+    if prof.get('csrc_sha') != csrc_sha():
+        return None, ent, 'stale: captured with kernel sources %s, running %s' % (prof.get('csrc_sha'), csrc_sha())
+    if fused_kernel_name(CONFIGS[cfg_name]) not in ent.get('kernel', ''):
+        return None, ent, 'capture is of %s, not of %s' % (ent.get('kernel'), fused_kernel_name(CONFIGS[cfg_name]))
+    return ent.get('dram_bytes'), ent, 'ncu --set full capture of this source state (profiles/ncu_latest.json)'
+
+
+class StepRunner(object):
+    """A Workload replayed as CUDA graphs, optionally with the path's collective (sfm_allreduce_partials) captured
+    with every step:
+      mode 'inline'   the all-reduce of step k's partials follows step k's epilogue on the same stream (the next step
+                      starts after it: its latency is exposed every step);
+      mode 'overlap'  the graph of step k forks a branch that all-reduces the partials of step k-1 (another buffer set)
+                      while step k's kernels run, and joins it at the end -- the way a trainer consumes the reduced
+                      losses one iteration late; `finish()` reduces the last step's partials, so every step's partials
+                      are reduced inside the timed interval."""
+
+    def __init__(self, wl, comm=None, mode='inline'):
+        self.wl, self.comm = wl, comm
+        self.mode = mode if comm is not None else None
+        self.graphs = None
+        self.last = None
+        if self.mode == 'overlap':
+            torch = wl.torch
+            self.side2 = torch.cuda.Stream()
+
+    def _allreduce(self, k, stream):
+        wl = self.wl
+        t = wl.sets[k % wl.nsets]
+        wl.L.check(wl.lib.sfm_allreduce_partials(self.comm._comm, C.c_void_p(t['losses'].data_ptr()), 5, C.c_void_p(stream)))
+
+    def _launch(self, k, stream_obj):
+        torch = self.wl.torch
+        stream = stream_obj.cuda_stream
+        if self.mode == 'overlap':
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(stream_obj)
+            self.side2.wait_event(fork)
+            self._allreduce(k - 1, self.side2.cuda_stream)          # previous step's partials (another buffer set)
+            join.record(self.side2)
+            self.wl.launch(k, stream)
+            stream_obj.wait_event(join)
+        else:
+            self.wl.launch(k, stream)
+            if self.mode == 'inline':
+                self._allreduce(k, stream)
+
+    def capture(self):
+        torch = self.wl.torch
+        wl = self.wl
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(wl.nsets):
+                self._launch(k, side)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs = []
+        for k in range(wl.nsets):
+            g = torch.cuda.CUDAGraph()
+            # thread-local capture mode: torch's NCCL watchdog thread may query events while this thread captures
+            with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
+                self._launch(k, torch.cuda.current_stream())
+            graphs.append(g)
+        torch.cuda.synchronize()
+        self.graphs = graphs
+
+    def step(self, k):
+        if self.graphs is not None:
+            self.graphs[k % self.wl.nsets].replay()
+        else:
+            self._launch(k, self.wl.torch.cuda.current_stream())
+        self.last = k
+
+    def finish(self):
+        """overlap mode: the partials of the last step are still unreduced."""
+        if self.mode == 'overlap' and self.last is not None:
+            self._allreduce(self.last, self.wl.torch.cuda.current_stream().cuda_stream)
+
+    def time(self, steps, warmup, per_step=None, before_stop=None):
+        """ms per step between two CUDA events on the launching stream (all of a step's kernels, and the captured
+        all-reduce, are on it or joined into it); `before_stop` runs right before the stop event (e.g. waits for
+        side-stream work)."""
+        torch = self.wl.torch
+        for k in range(warmup):
+            self.step(k)
+            if per_step:
+                per_step(k)
+        self.finish()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(steps):
+            self.step(warmup + k)
+            if per_step:
+                per_step(warmup + k)
+        self.finish()
+        if before_stop:
+            before_stop()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, t0, time.perf_counter()
+
+    def reduced_rows_ok(self, world):
+        """Every rank holds the same synthetic snippets, so a reduced row of partials must be world x the local row.
+        Runs one rotation of the buffer sets (+1 step in overlap mode) and compares against plain local steps."""
+        torch = self.wl.torch
+        wl = self.wl
+        n = wl.nsets
+        for k in range(n + (1 if self.mode == 'overlap' else 0)):
+            self.step(k)
+        torch.cuda.synchronize()
+        red = wl.all_losses[:, :5].clone()
+        plain = StepRunner(wl)
+        for k in range(n):
+            plain.step(k)
+        torch.cuda.synchronize()
+        rows = slice(1, n) if self.mode == 'overlap' else slice(0, n)      # overlap: row 0 was rewritten by the extra step
+        return bool(torch.allclose(red[rows], wl.all_losses[rows, :5] * world, rtol=1e-5, atol=1e-8))
+
+
+def trace(msg):
+    if os.environ.get('SFM_BENCH_TRACE'):
+        sys.stderr.write('[bench rank %s %.1f] %s\n' % (os.environ.get('RANK', '0'), time.perf_counter() % 1000, msg))
+        sys.stderr.flush()
+
+
+def max_over_ranks(ms, device, world):
+    if world == 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_scaling_block(args, device, world, rank, comm, peak):
+    """The split the north star names: a FIXED global batch sharded by snippet.  Per workload: the
+    single-GPU time of the whole batch (measured on every rank, the slowest is reported), then the shard of 1/N of
+    it per GPU (i) with no collective, (ii) with the 5-float loss all-reduce of every step captured behind the step
+    (its latency exposed), (iii) with that all-reduce captured as a parallel branch of the NEXT step's graph (hidden
+    behind the kernels), (iv) as (iii) with a 159.5 MB fp32 all-reduce -- the size of the DispNet + PoseNet gradient
+    (39.9 M parameters) -- issued every step on NCCL's own stream next to it, the way the trainer's
+    gradient exchange would run; every interval ends when all of its collectives have finished."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    names = ['cfg4'] + (['cfg5'] if world >= 8 else [])
+    steps = max(20, min(args.steps, 200))
+    for name in names:
+        c = CONFIGS[name]
+        Bg = c['B']
+        if Bg % world:
+            out[name] = dict(skipped='global batch %d is not divisible by %d ranks' % (Bg, world))
+            continue
+        ent = dict(workload=describe(name), global_batch=Bg, per_gpu_batch=Bg // world, steps=steps)
+        # ---- one GPU, whole batch
+        w1 = Workload(name, device)
+        r1 = StepRunner(w1)
+        r1.capture()
+        ms1, _, _ = r1.time(steps, 5)
+        ms1 = max_over_ranks(ms1, device, world)
+        ent['single_gpu_us_per_step'] = ms1 * 1e3
+        del r1, w1
+        torch.cuda.empty_cache()
+        # ---- the shard
+        wl = Workload(name, device, B_global=Bg, B_local=Bg // world)
+        dist.barrier()
+        res = {}
+        for mode in ('no_collective', 'loss_allreduce_inline', 'loss_allreduce_overlapped', 'loss_allreduce_overlapped_plus_159MB_gradient_allreduce'):
+            cm = comm if mode != 'no_collective' else None
+            rmode = 'inline' if mode == 'loss_allreduce_inline' else 'overlap'
+            runner = StepRunner(wl, cm, rmode)
+            how = {'inline': 'all-reduce of step k captured behind step k\'s epilogue (exposed)',
+                   'overlap': 'all-reduce of step k-1 captured as a parallel branch of step k\'s graph'}[rmode]
+            try:
+                runner.capture()
+            except Exception as exc:                                   # noqa: BLE001 -- NCCL refused the capture: call it per step
+                runner = StepRunner(wl, cm, 'inline')
+                how = 'direct call per step (graph capture failed: %s)' % str(exc)[:80]
+            per_step, before_stop = None, None
+            if mode.endswith('gradient_allreduce'):
+                grad = torch.zeros(39_880_000, device=device)           # 159.5 MB fp32 (SURVEY 7.6)
+                works = []
+
+                def per_step(k, grad=grad, works=works):
+                    if len(works) >= 2:
+                        works.pop(0).wait()
+                    works.append(dist.all_reduce(grad, async_op=True))
+
+                def before_stop(works=works):
+                    while works:
+                        works.pop(0).wait()                             # the compute stream waits for NCCL's stream
+            dist.barrier()
+            torch.cuda.synchronize()
+            trace('%s %s: timing' % (name, mode))
+            ms, _, _ = runner.time(steps, 5, per_step, before_stop)
+            ms = max_over_ranks(ms, device, world)
+            res[mode] = dict(us_per_step=ms * 1e3, global_mpix_s=Bg * pyramid_pixels(c['H'], c['W']) / (ms * 1e-3) / 1e6,
+                             efficiency_vs_single_gpu=ms1 / (world * ms), collective=how if cm is not None else None)
+            if mode in ('loss_allreduce_inline', 'loss_allreduce_overlapped'):
+                res[mode]['reduced_equals_world_x_local'] = runner.reduced_rows_ok(world)
+            del runner
+            if mode.endswith('gradient_allreduce'):
+                del grad
+        ent.update(res)
+        ent['roofline_per_gpu_us'] = bytes_strict(Bg // world, c['S'], c['H'], c['W'], c['exp_reg'] != 0) / peak / 1e3
+        out[name] = ent
+        del wl
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from sfm_learner_chainer_b200.distributed import allreduce_loss_partials
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus != world:
+        raise SystemExit('bench.py: --gpus %d but WORLD_SIZE=%d: launch N > 1 as `python -m torch.distributed.run --nnodes=1 '
+                         '--nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...` (one process per GPU)' % (args.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the view-synthesis loss path has no CPU fallback)')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    comm = None
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
+        from sfm_learner_chainer_b200.distributed import LossPartialsComm
+        comm = LossPartialsComm(rank, world)                 # the C ABI's own NCCL communicator (sfm_comm_create)
     n_gpus = world
     peak, peak_src = measured_peak()
 
     c = CONFIGS[args.config]
     wl = Workload(args.config, device, B_global=c['B'] * world)
+    use_comm = comm if (world > 1 and not args.no_allreduce) else None
+    runner = StepRunner(wl, use_comm, 'overlap')
+    collective_how = None
     if not args.no_graph:
-        wl.capture()
+        try:
+            runner.capture()
+            collective_how = ('the all-reduce of step k-1 is a parallel branch of step k\'s CUDA graph; the last step\'s is issued '
+                              'before the stop event') if use_comm else None
+        except Exception as exc:                              # noqa: BLE001 -- NCCL refused the capture
+            if use_comm is None:
+                raise
+            runner = StepRunner(wl, use_comm, 'inline')       # direct calls: step, then its all-reduce, on one stream
+            collective_how = 'direct C-ABI calls, all-reduce after every step (graph capture failed: %s)' % str(exc)[:80]
+    elif use_comm:
+        runner = StepRunner(wl, use_comm, 'inline')
+        collective_how = 'direct call after every step'
 
-    # Loss partials (the path's only cross-rank quantity, reporting only -- gradients are final per rank): every
-    # step's five partials are summed over the ranks.  --allreduce-every 1 issues one NCCL call per step; the
-    # default batches the partials of `nsets` consecutive steps (one row per step, snapshot first so that later
-    # steps can overwrite their rows) into one asynchronous call, the way a trainer that reports every few
-    # iterations would.  At ~48 us per step the per-step call is host-bound (measured at N=2: 52.0 vs 47.1 us).
-    pending = []
-    every = args.allreduce_every if args.allreduce_every > 0 else max(1, min(wl.nsets, args.steps))   # >= 1 call inside the timed region
-    staging = [torch.zeros_like(wl.all_losses) for _ in range(2)]
-    flip = [0]
-
-    def per_step(k):
-        if world == 1 or args.no_allreduce:
-            return
-        if every == 1:
-            pending.append(allreduce_loss_partials(wl.sets[k % wl.nsets]['losses'][:5], async_op=True))
-        elif (k + 1) % every == 0:
-            buf = staging[flip[0]]
-            flip[0] ^= 1
-            buf.copy_(wl.all_losses)             # ordered after the steps that wrote the rows (same stream)
-            pending.append(allreduce_loss_partials(buf, async_op=True))
-        if len(pending) > 2 and every > 1 or len(pending) > 64:
-            pending.pop(0).wait()
-
+    trace('captured: %s' % collective_how)
     sampler = ClockSampler(local)
     sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms, t0, t1 = wl.time_steps(args.steps, args.warmup, per_step if world > 1 else None)
-    for w in pending:
-        w.wait()
+    ms, t0, t1 = runner.time(args.steps, args.warmup)
     torch.cuda.synchronize()
-    allreduce_ok = None
-    if world > 1 and not args.no_allreduce and every > 1 and pending:
-        # every rank holds the same synthetic snippets, so the reduced partials must be world x the local ones
-        red = staging[flip[0] ^ 1][:, :5]
-        allreduce_ok = bool(torch.allclose(red, wl.all_losses[:, :5] * world, rtol=1e-5, atol=1e-8))
+    trace('timed %.4f ms' % ms)
+    allreduce_ok = runner.reduced_rows_ok(world) if use_comm is not None else None
+    trace('check %s' % allreduce_ok)
     if world > 1:
         dist.barrier()
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # keep the GPU busy a little longer if the timed region was too short for a clock sample
-    if t1 - t0 < 0.05:
-        tt = time.perf_counter()
-        k = 0
-        while time.perf_counter() - tt < 0.1:
-            wl.step(k)
-            k += 1
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
+    ms = max_over_ranks(ms, device, world)
+    # The timed region is short (K steps of ~40 us under the driver's flags); the identical steps keep running for
+    # ~0.25 s right after it so that the 10 ms clock sampler sees the GPU under this load.
+    t_region = t1 - t0
+    n_fill = int(min(20000, max(1, 0.25 / (ms * 1e-3))))    # the same count on every rank (ms is the max over ranks): the steps carry a collective
+    for k in range(n_fill):
+        runner.step(k)
+        if k % 64 == 63:
+            torch.cuda.synchronize()
+    runner.finish()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     sampler.stop()
     clocks = sampler.summary(t0, t1)
+    clocks['window'] = ('the timed region (%.1f ms) plus %.0f ms of the identical steps run right after it: the sampler polls '
+                        'every 10 ms' % (t_region * 1e3, (t1 - t0 - t_region) * 1e3))
 
     total_pix = wl.pix * world
     value = total_pix / (ms * 1e-3) / 1e6
-    n_launch = 3 + (1 if c['smooth_reg'] else 0)       # prep, [smooth], fused, epilogue
+    n_launch = 3                                             # prologue (pyramid + tables + smoothness tasks), fused loss, epilogue
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='%s: %s' % (args.config, describe(args.config)), per_gpu_batch=wl.B,
-                            global_batch=wl.B * world, sources=wl.S, H=wl.H, W=wl.W, n_scales=4,
-                            parallelism=('snippet-sharded x%d, no data-path collective; loss partials of every step all-reduced '
-                                         'asynchronously over NCCL, %s' % (world, 'one call per step' if every == 1 else
-                                                                           '%d steps per call' % every)) if world > 1 else 'single GPU',
-                            l2_policy='inputs+outputs rotated over %d buffer sets (%.0f MB > 2 x L2 %.0f MB)' % (
-                                wl.nsets, wl.nsets * wl.A_strict / 1e6, wl.l2_bytes / 1e6),
-                            launch=('CUDA graph replay of the step\'s %d kernel nodes (pyramid/tables, %sfused loss, epilogue; '
-                                    'programmatic dependent launches between them)' % (n_launch, 'smoothness, ' if c['smooth_reg'] else ''))
+                config=config_dict(args.config, world),
+                timing=dict(buffer_sets=wl.nsets, rotation_mb=wl.nsets * wl.A_strict / 1e6, l2_mb=wl.l2_bytes / 1e6,
+                            launch=('CUDA graph replay of the step\'s %d kernel nodes (prologue: pyramid + tables + smoothness tasks; '
+                                    'fused loss; epilogue; programmatic dependent launches between them)' % n_launch)
                             if not args.no_graph else 'direct C-ABI calls',
-                            units='target-pyramid pixels = B * sum_s h_s*w_s (%d per step per GPU)' % wl.pix),
+                            parallelism=('snippet-sharded x%d (weak scaling: %d snippets per GPU, B_global = %d), no data-path '
+                                         'collective; the five loss partials of EVERY step all-reduced over NCCL by '
+                                         'sfm_allreduce_partials inside the timed event interval, %s' % (
+                                             world, wl.B, wl.B * world, collective_how)) if world > 1 else 'single GPU',
+                            timer='CUDA events on the launching stream around the K steps, barrier + synchronize on both sides, max over ranks'),
                 clocks=clocks, gpu_launches=n_launch * args.steps)
     if allreduce_ok is not None:
         line['loss_allreduce_check'] = allreduce_ok
@@ -557,51 +765,41 @@ def run_b200(args):
     if rank == 0:
         # ---- roofline of the dominant kernel (fused loss), events around the kernel itself
         k_mean, k_med = wl.time_fused_kernel(200)
-        ach = wl.A_kernel / (k_mean * 1e-3) / 1e9
-        traffic, issue = None, None
-        try:
-            prof = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_latest.json')))[args.config]
-            traffic = prof.get('dram_bytes')             # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-            issue = prof
-        except Exception:
-            pass
+        ach = wl.A_strict / (k_mean * 1e-3) / 1e9
+        traffic, ncu_ent, traffic_note = ncu_traffic(args.config)
         line['roofline'] = dict(bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic,
-                                kernel='sfm_fused_%s_kernel' % ('ssim' if (c['ssim_rate'] and not c['exp_reg']) else 'l1'),
-                                kernel_us=k_mean * 1e3, kernel_us_median=k_med * 1e3,
-                                algorithmic_bytes=wl.A_kernel, peak_source=peak_src,
-                                byte_model='4*B*sum_hw*(3 + 3S + 2 + exp*2S): NHWC4 pyramid in, disp in, gdisp out (+logits/glogits)',
-                                note='at B=4 the roofline time is ~2 us (below launch latency): latency-bound; '
-                                     'see other_configs for the bandwidth-relevant shapes.  The fused kernels are '
-                                     'FP32-issue bound, not HBM bound (DESIGN.md section 5): ncu of the same kernel in '
-                                     'profiles/ncu_latest.json',
-                                ncu=issue)
+                                kernel=fused_kernel_name(c), kernel_us=k_mean * 1e3, kernel_us_median=k_med * 1e3,
+                                algorithmic_bytes=wl.A_strict, peak_source=peak_src,
+                                byte_model='SURVEY 8(d) A-strict (the whole step\'s compulsory bytes: full-res images once + disp r/w + '
+                                           'logits r/w + poses + K) over the fused kernel\'s own duration',
+                                kernel_model=dict(algorithmic_bytes=wl.A_kernel, frac=wl.A_kernel / (k_mean * 1e-3) / 1e9 / peak,
+                                                  byte_model='secondary model of SURVEY 8(d): 4*B*sum_hw*(3 + 3S + 2 + exp*2S), '
+                                                             'the images of every scale as the kernel\'s input'),
+                                traffic_source=traffic_note, ncu=ncu_ent,
+                                note='at B=4 the roofline time is ~1.5 us (below one launch): latency-bound by construction; '
+                                     'other_configs holds the bandwidth-relevant shapes.  The fused kernels are issue-bound '
+                                     '(SSIM) / issue- and L1-wavefront-bound (L1), not HBM-bound (DESIGN.md section 5)')
         ach_s = wl.A_strict / (ms * 1e-3) / 1e9
         line['roofline_step'] = dict(bound='hbm', achieved=ach_s, peak=peak, unit='GB/s', frac=ach_s / peak,
                                      algorithmic_bytes=wl.A_strict,
                                      byte_model='A-strict: full-res images once + disp r/w + logits r/w + poses + K')
         line['step_share_of_fused_kernel'] = k_mean / ms if world == 1 else None
+    del runner
     if world == 1:
-        # ---- the same steps with the next batch's pyramid overlapped (extra figure; `value` stays the sequential step)
-        if not args.no_other and not args.no_graph:
-            try:
-                pms = wl.time_pipelined(min(args.steps, 1000), args.warmup)
-                line['pipelined'] = dict(value=wl.pix / (pms * 1e-3) / 1e6, unit=UNIT, ms_per_step=pms,
-                                         note='sfm_pyramid of batch k+1 on a side stream while sfm_loss_forward_backward('
-                                              'SFM_FLAG_REUSE_PYRAMID) of batch k runs; the pyramid depends on the input images only')
-            except Exception as exc:                          # noqa: BLE001 -- an extra figure must not take the line down
-                line['pipelined'] = dict(error=str(exc)[:200])
-        # ---- e2e through the host-buffer C-ABI entry point
-        e2e_steps = max(5, min(200, args.steps))
-        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device, n_ctx=3)
-        ev1, _, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=1)
-        ev8, h2d8, _, _ = run_e2e(args.config, e2e_steps, device, n_ctx=3, u8=True)
-        line['e2e'] = dict(value=ev, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
-                           api='sfm_loss_step_host_submit/_wait, three host contexts used in rotation (pinned host buffers; every step: '
-                               'H2D of all inputs, pyramid + fused fwd+bwd, D2H of losses and all gradients)',
-                           synchronous_value=ev1, synchronous_api='sfm_loss_step_host (one step at a time)',
-                           u8_frames_value=ev8, u8_frames_h2d_bytes_per_step=h2d8,
-                           u8_frames_api='sfm_loss_step_host_u8_submit/_wait: decoded uint8 frames + augmentation draws in, '
-                                         'normalisation / random scale-crop-flip / multi-scale intrinsics on the device (data-layer fusion)')
+        # ---- e2e through the host-buffer C-ABI entry point (primary: the uint8-frame data layer the reference really has)
+        e8 = run_e2e(args.config, device, n_ctx=3, u8=True)
+        ef = run_e2e(args.config, device, n_ctx=3)
+        es = run_e2e(args.config, device, n_ctx=1, repeats=1)
+        line['e2e'] = dict(value=e8['value'], unit=UNIT, h2d_bytes_per_step=e8['h2d'], d2h_bytes_per_step=e8['d2h'],
+                           steps_per_repeat=e8['steps'], repeats=e8['repeats'], h2d_gbs=e8['h2d_gbs'],
+                           api='sfm_loss_step_host_u8_submit/_wait, three host contexts in rotation (pinned host buffers; every step: '
+                               'H2D of the decoded uint8 frames, K, augmentation draws, disparities, poses; ingest + prologue + fused '
+                               'fwd+bwd + epilogue; D2H of the five losses and every gradient).  Median of three repeats of '
+                               '>= 200 steps and >= 0.5 s each',
+                           float_images=dict(value=ef['value'], h2d_bytes_per_step=ef['h2d'], d2h_bytes_per_step=ef['d2h'],
+                                             repeats=ef['repeats'], h2d_gbs=ef['h2d_gbs'],
+                                             api='sfm_loss_step_host_submit/_wait: float32 images in (4 bytes per sample), three contexts'),
+                           synchronous=dict(value=es['value'], api='sfm_loss_step_host, one step at a time, float32 images'))
         # ---- other single-GPU BASELINE shapes, device timed
         if not args.no_other:
             others = {}
@@ -617,7 +815,8 @@ def run_b200(args):
                 others[name] = dict(workload=describe(name), ms_per_step=oms, value=w2.pix / (oms * 1e-3) / 1e6, unit=UNIT,
                                     step_frac_of_hbm_peak=w2.A_strict / (oms * 1e-3) / 1e9 / peak,
                                     fused_kernel_us=km * 1e3,
-                                    fused_kernel_frac_of_hbm_peak=w2.A_kernel / (km * 1e-3) / 1e9 / peak)
+                                    fused_kernel_frac_of_hbm_peak=w2.A_strict / (km * 1e-3) / 1e9 / peak,
+                                    fused_kernel_frac_kernel_model=w2.A_kernel / (km * 1e-3) / 1e9 / peak)
                 del w2
                 torch.cuda.empty_cache()
             line['other_configs'] = others
@@ -626,22 +825,33 @@ def run_b200(args):
             n_iters = 12 if args.config in ('cfg1', 'cfg2') else 1
             sec, threads, (B, S, H, W) = cpu_oracle_run(args.config, n_iters, 1)
             line['cpu_baseline'] = dict(value=B * pyramid_pixels(H, W) / sec / 1e6, unit=UNIT, cores=threads, kind='port',
-                                        sample='%d full %s steps of the numpy oracle (scalar port, 1 thread), median' % (n_iters, args.config),
+                                        sample='%d full %s steps of the numpy oracle (scalar port, 1 thread), mean' % (n_iters, args.config),
                                         ms_per_step=sec * 1e3)
     else:
-        # e2e at N GPUs: every rank runs the host-buffer path on its shard; aggregate = sum / max time
-        e2e_steps = max(5, min(100, args.steps))
+        # e2e at N GPUs: every rank runs the host-buffer path on its shard; aggregate = total pixels / slowest rank
+        trace('e2e')
         dist.barrier()
-        ev, h2d, d2h, _ = run_e2e(args.config, e2e_steps, device)
-        t = torch.tensor([wl.pix / ev], device=device)      # us per step on this rank (pix / Mpix/s)
+        e8 = run_e2e(args.config, device, n_ctx=3, u8=True, repeats=3)
+        t = torch.tensor([wl.pix / e8['value']], device=device)      # us per step on this rank (pix / Mpix/s)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        line['e2e'] = dict(value=total_pix / float(t.item()), unit=UNIT, h2d_bytes_per_step=h2d * world,
-                           d2h_bytes_per_step=d2h * world, steps=e2e_steps,
-                           api='sfm_loss_step_host on every rank (its snippet shard)')
+        line['e2e'] = dict(value=total_pix / float(t.item()), unit=UNIT, h2d_bytes_per_step=e8['h2d'] * world,
+                           d2h_bytes_per_step=e8['d2h'] * world, steps_per_repeat=e8['steps'],
+                           api='sfm_loss_step_host_u8_submit/_wait on every rank (its snippet shard, three host contexts); '
+                               'median of three repeats of >= 200 steps and >= 0.5 s; total pixels / slowest rank')
+        del wl
+        torch.cuda.empty_cache()
+        if not args.no_other:
+            ss = strong_scaling_block(args, device, world, rank, comm, peak)
+            if rank == 0:
+                line['strong_scaling'] = ss
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            import gc
+            gc.collect()                                       # graphs that captured the all-reduce go first
+            comm.close()
         dist.destroy_process_group()
 
 
@@ -653,12 +863,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
     ap.add_argument('--no-graph', action='store_true', help='direct C-ABI calls instead of CUDA graph replay')
-    ap.add_argument('--no-other', action='store_true', help='skip the other_configs sweep')
+    ap.add_argument('--no-other', action='store_true', help='skip the other_configs sweep (N = 1) / the strong_scaling block (N > 1)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-allreduce', action='store_true', help='(diagnostic) skip the loss-partial allreduce at N > 1')
-    ap.add_argument('--allreduce-every', type=int, default=0,
-                    help='N > 1: all-reduce the loss partials every K steps (K rows in one call); 1 = one call per step; '
-                         '0 (default) = one call per rotation of the buffer sets')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -266,7 +266,8 @@ int sfm_loss_step_host_u8_submit(SfmHostCtx* ctx, const uint8_t* frames, const f
  *   every step:  sfm_allreduce_partials(comm, losses, 5, stream)   in place on the device array `losses`; enqueued on
  *                                                     `stream` (after the loss call that wrote it), asynchronous,
  *                                                     capturable in a CUDA graph together with the step
- *   at the end:  sfm_comm_destroy(comm)                                                                          */
+ *   at the end:  sfm_comm_destroy(comm)           after every CUDA graph that captured the all-reduce has been destroyed
+ *                                                 (such a graph holds a reference on the NCCL communicator)          */
 #define SFM_NCCL_UNIQUE_ID_BYTES 128
 typedef struct SfmComm SfmComm;
 int sfm_nccl_set_library(const char* path);

@@ -48,6 +48,9 @@ class LossPartialsComm(object):
 
         comm = LossPartialsComm(rank, world)            # collective: every rank calls it, on its own device
         comm.allreduce(losses_dev, stream)              # in place, asynchronous on `stream`, graph-capturable
+        comm.close()                                    # after every CUDA graph that captured allreduce() is destroyed:
+                                                        # such a graph holds a reference on the NCCL communicator and
+                                                        # ncclCommDestroy waits for it
     """
 
     def __init__(self, rank, world_size, exchange=None, nccl_library=None):

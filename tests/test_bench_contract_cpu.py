@@ -23,6 +23,9 @@ def test_reference_arm_prints_the_contract_line():
     assert line['cpu_baseline']['cores'] >= 1 and 'sample' in line['cpu_baseline']
     assert line['e2e'] == dict(value=line['value'], unit='Mpix/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert line['gpu_launches'] == 0 and line['config']['workload'].startswith('cfg1')
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line['config'] == bench.config_dict('cfg1', 1)          # the same `config` object as the B200 arm prints
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -36,7 +39,8 @@ def test_b200_arm_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip('a CUDA device is present')
-    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '3'], stdout=subprocess.PIPE,
+    env = {k: v for k, v in os.environ.items() if k not in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK')}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '3'], stdout=subprocess.PIPE, env=env,
                          stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert 'no CUDA device' in (out.stderr + out.stdout) and 'no CPU fallback' in (out.stderr + out.stdout)
@@ -51,3 +55,10 @@ def test_byte_models_match_survey_section_8d():
     assert abs(bench.bytes_strict(32, 4, 128, 416, True) / (8 * pix) - 85.2) < 0.05       # A-strict, S=4, exp
     assert bench.bytes_fused_kernel(4, 2, 128, 416, False) == 44 * pix                    # kernel model 44 B/pix
     assert bench.bytes_fused_kernel(32, 4, 128, 416, True) == 100 * 8 * pix               # 100 B/pix
+
+
+def test_b200_arm_rejects_a_gpu_count_that_is_not_the_world_size():
+    env = {k: v for k, v in os.environ.items() if k not in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK')}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--gpus', '2', '--steps', '3'], stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode != 0 and 'torch.distributed.run' in (out.stderr + out.stdout)

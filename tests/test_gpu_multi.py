@@ -45,14 +45,21 @@ def _worker(rank, world, port, out_dir, B):
     with torch.cuda.stream(side):
         l3, g3, _ = op2.forward_backward(*args)            # warm-up on the capture stream
         side.synchronize()
-        with torch.cuda.graph(graph, stream=side):
+        # thread-local capture mode: torch's NCCL watchdog thread may query events while this thread captures
+        with torch.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
             l3, g3, _ = op2.forward_backward(*args)
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize()
+    l3_host = l3.cpu().numpy()
+    # a graph that captured the all-reduce holds a reference on the NCCL communicator: destroy it before the communicator
+    # (ncclCommDestroy waits for such references)
+    del graph, g3
+    import gc
+    gc.collect()
     lo, hi = shard_range(B, rank, world)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), losses=losses.cpu().numpy(), gposes=grads['gposes'].cpu().numpy(),
-             gdisp0=grads['gdisps'][0].cpu().numpy(), lo=lo, hi=hi, losses_abi=l2.cpu().numpy(), losses_graph=l3.cpu().numpy(),
+             gdisp0=grads['gdisps'][0].cpu().numpy(), lo=lo, hi=hi, losses_abi=l2.cpu().numpy(), losses_graph=l3_host,
              gdisp0_abi=g2['gdisps'][0].cpu().numpy(), B_global=op2.op.B_global)
     comm.close()
     dist.destroy_process_group()
@@ -68,7 +75,14 @@ def test_sharded_result_equals_single_gpu_result(tmp_path):
     from tests.gpu_util import dev_inputs, host, assert_grad_close
     world, B = 2, 5                                   # uneven shards: 3 + 2
     port = 29600 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, str(tmp_path), B), nprocs=world, join=True)
+    ctx = mp.spawn(_worker, args=(world, port, str(tmp_path), B), nprocs=world, join=False)
+    import time
+    deadline = time.time() + 240                       # a stuck collective must not eat the GPU budget
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for pr in ctx.processes:
+                pr.kill()
+            pytest.fail('multi-GPU workers did not finish within 240 s')
     d = make_snippets(B, 2, 128, 416, seed=90)
     g = dev_inputs(d)
     lf, gf = ViewSynthesisLoss(**FLAGS).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], None)
