@@ -261,10 +261,14 @@ class Workload(object):
             self.sets.append(t)
         self.graphs = None
 
-    def launch(self, k, stream):
+    def launch(self, k, stream, peer=None):
         t = self.sets[k % self.nsets]
-        rc = self.lib.sfm_loss_forward_backward(C.byref(self.desc), C.byref(t['inp']), C.c_void_p(t['losses'].data_ptr()),
-                                                C.byref(t['g']), t['wsp'], C.c_void_p(stream))
+        if peer is not None:      # the epilogue kernel completes the five losses across the ranks over NVLink peer memory
+            rc = self.lib.sfm_loss_forward_backward_peer(C.byref(self.desc), C.byref(t['inp']), C.c_void_p(t['losses'].data_ptr()),
+                                                         C.byref(t['g']), t['wsp'], peer.handle, C.c_void_p(stream))
+        else:
+            rc = self.lib.sfm_loss_forward_backward(C.byref(self.desc), C.byref(t['inp']), C.c_void_p(t['losses'].data_ptr()),
+                                                    C.byref(t['g']), t['wsp'], C.c_void_p(stream))
         if rc:
             self.L.check(rc)
 
@@ -473,7 +477,9 @@ class StepRunner(object):
       mode 'overlap'  the graph of step k forks a branch that all-reduces the partials of step k-1 (another buffer set)
                       while step k's kernels run, and joins it at the end -- the way a trainer consumes the reduced
                       losses one iteration late; `finish()` reduces the last step's partials, so every step's partials
-                      are reduced inside the timed interval."""
+                      are reduced inside the timed interval;
+      mode 'peer'     no collective call at all: `comm` is a PeerLossSum and the step's own epilogue kernel sums the
+                      partials over NVLink peer memory (sfm_loss_forward_backward_peer)."""
 
     def __init__(self, wl, comm=None, mode='inline'):
         self.wl, self.comm = wl, comm
@@ -500,6 +506,8 @@ class StepRunner(object):
             join.record(self.side2)
             self.wl.launch(k, stream)
             stream_obj.wait_event(join)
+        elif self.mode == 'peer':
+            self.wl.launch(k, stream, self.comm)
         else:
             self.wl.launch(k, stream)
             if self.mode == 'inline':
@@ -596,14 +604,15 @@ def max_over_ranks(ms, device, world):
     return float(t.item())
 
 
-def strong_scaling_block(args, device, world, rank, comm, peak):
+def strong_scaling_block(args, device, world, rank, comm, peer, peak):
     """The split the north star names: a FIXED global batch sharded by snippet.  Per workload: the
     single-GPU time of the whole batch (measured on every rank, the slowest is reported), then the shard of 1/N of
-    it per GPU (i) with no collective, (ii) with the 5-float loss all-reduce of every step captured behind the step
-    (its latency exposed), (iii) with that all-reduce captured as a parallel branch of the NEXT step's graph (hidden
-    behind the kernels), (iv) as (iii) with a 159.5 MB fp32 all-reduce -- the size of the DispNet + PoseNet gradient
-    (39.9 M parameters) -- issued every step on NCCL's own stream next to it, the way the trainer's
-    gradient exchange would run; every interval ends when all of its collectives have finished."""
+    it per GPU (i) with no collective, (ii) with the five loss partials summed across the ranks inside every step's
+    epilogue kernel over NVLink peer memory (the product path: no collective call), (iii) with an NCCL all-reduce of
+    every step captured behind the step (its latency exposed), (iv) with that all-reduce captured as a parallel
+    branch of the NEXT step's graph, (v) as (ii) with a 159.5 MB fp32 all-reduce -- the size of the DispNet + PoseNet
+    gradient (39.9 M parameters) -- issued every step on NCCL's own stream next to it, the way the
+    trainer's gradient exchange would run; every interval ends when all of its collectives have finished."""
     import torch
     import torch.distributed as dist
     out = {}
@@ -629,12 +638,14 @@ def strong_scaling_block(args, device, world, rank, comm, peak):
         wl = Workload(name, device, B_global=Bg, B_local=Bg // world)
         dist.barrier()
         res = {}
-        for mode in ('no_collective', 'loss_allreduce_inline', 'loss_allreduce_overlapped', 'loss_allreduce_overlapped_plus_159MB_gradient_allreduce'):
-            cm = comm if mode != 'no_collective' else None
-            rmode = 'inline' if mode == 'loss_allreduce_inline' else 'overlap'
+        for mode in ('no_collective', 'loss_sum_in_epilogue_kernel_over_peer_memory', 'nccl_allreduce_inline', 'nccl_allreduce_overlapped',
+                     'loss_sum_in_epilogue_kernel_plus_159MB_gradient_allreduce'):
+            rmode = 'peer' if mode.startswith('loss_sum_in_epilogue') else ('inline' if mode == 'nccl_allreduce_inline' else 'overlap')
+            cm = None if mode == 'no_collective' else (peer if rmode == 'peer' else comm)
             runner = StepRunner(wl, cm, rmode)
-            how = {'inline': 'all-reduce of step k captured behind step k\'s epilogue (exposed)',
-                   'overlap': 'all-reduce of step k-1 captured as a parallel branch of step k\'s graph'}[rmode]
+            how = {'inline': 'NCCL all-reduce of step k captured behind step k\'s epilogue (exposed)',
+                   'overlap': 'NCCL all-reduce of step k-1 captured as a parallel branch of step k\'s graph',
+                   'peer': 'no collective call: the epilogue kernel of every step exchanges the partials over NVLink peer memory'}[rmode]
             try:
                 runner.capture()
             except Exception as exc:                                   # noqa: BLE001 -- NCCL refused the capture: call it per step
@@ -660,7 +671,7 @@ def strong_scaling_block(args, device, world, rank, comm, peak):
             ms = max_over_ranks(ms, device, world)
             res[mode] = dict(us_per_step=ms * 1e3, global_mpix_s=Bg * pyramid_pixels(c['H'], c['W']) / (ms * 1e-3) / 1e6,
                              efficiency_vs_single_gpu=ms1 / (world * ms), collective=how if cm is not None else None)
-            if mode in ('loss_allreduce_inline', 'loss_allreduce_overlapped'):
+            if not mode.endswith('gradient_allreduce') and cm is not None:
                 res[mode]['reduced_equals_world_x_local'] = runner.reduced_rows_ok(world)
             del runner
             if mode.endswith('gradient_allreduce'):
@@ -686,33 +697,24 @@ def run_b200(args):
         raise SystemExit('bench.py: no CUDA device (the view-synthesis loss path has no CPU fallback)')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
-    comm = None
+    comm = peer = None
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
         from sfm_learner_chainer_b200.distributed import LossPartialsComm
-        comm = LossPartialsComm(rank, world)                 # the C ABI's own NCCL communicator (sfm_comm_create)
+        comm = LossPartialsComm(rank, world)                 # the C ABI's NCCL communicator (sfm_comm_create): the library-call baseline
+        from sfm_learner_chainer_b200.distributed import PeerLossSum
+        peer = PeerLossSum(rank, world)                      # slot arrays for the in-kernel sum over NVLink peer memory
     n_gpus = world
     peak, peak_src = measured_peak()
 
     c = CONFIGS[args.config]
     wl = Workload(args.config, device, B_global=c['B'] * world)
-    use_comm = comm if (world > 1 and not args.no_allreduce) else None
-    runner = StepRunner(wl, use_comm, 'overlap')
-    collective_how = None
+    use_comm = peer if (world > 1 and not args.no_allreduce) else None
+    runner = StepRunner(wl, use_comm, 'peer')
+    collective_how = ('summed across the ranks inside every step\'s epilogue kernel over NVLink peer memory '
+                      '(sfm_loss_forward_backward_peer; no collective call, no extra launch)') if use_comm else None
     if not args.no_graph:
-        try:
-            runner.capture()
-            collective_how = ('the all-reduce of step k-1 is a parallel branch of step k\'s CUDA graph; the last step\'s is issued '
-                              'before the stop event') if use_comm else None
-        except Exception as exc:                              # noqa: BLE001 -- NCCL refused the capture
-            if use_comm is None:
-                raise
-            runner = StepRunner(wl, use_comm, 'inline')       # direct calls: step, then its all-reduce, on one stream
-            collective_how = 'direct C-ABI calls, all-reduce after every step (graph capture failed: %s)' % str(exc)[:80]
-    elif use_comm:
-        runner = StepRunner(wl, use_comm, 'inline')
-        collective_how = 'direct call after every step'
-
+        runner.capture()
     trace('captured: %s' % collective_how)
     sampler = ClockSampler(local)
     sampler.start()
@@ -754,8 +756,7 @@ def run_b200(args):
                                     'fused loss; epilogue; programmatic dependent launches between them)' % n_launch)
                             if not args.no_graph else 'direct C-ABI calls',
                             parallelism=('snippet-sharded x%d (weak scaling: %d snippets per GPU, B_global = %d), no data-path '
-                                         'collective; the five loss partials of EVERY step all-reduced over NCCL by '
-                                         'sfm_allreduce_partials inside the timed event interval, %s' % (
+                                         'collective call; the five loss partials of EVERY step are %s' % (
                                              world, wl.B, wl.B * world, collective_how)) if world > 1 else 'single GPU',
                             timer='CUDA events on the launching stream around the K steps, barrier + synchronize on both sides, max over ranks'),
                 clocks=clocks, gpu_launches=n_launch * args.steps)
@@ -841,7 +842,7 @@ def run_b200(args):
         del wl
         torch.cuda.empty_cache()
         if not args.no_other:
-            ss = strong_scaling_block(args, device, world, rank, comm, peak)
+            ss = strong_scaling_block(args, device, world, rank, comm, peer, peak)
             if rank == 0:
                 line['strong_scaling'] = ss
     if rank == 0:
@@ -852,6 +853,8 @@ def run_b200(args):
             import gc
             gc.collect()                                       # graphs that captured the all-reduce go first
             comm.close()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

@@ -277,6 +277,26 @@ int sfm_comm_create(const void* unique_id, int nranks, int rank, SfmComm** comm_
 int sfm_comm_destroy(SfmComm* comm);
 int sfm_allreduce_partials(SfmComm* comm, float* losses, int count, void* stream);
 
+/* The same sum WITHOUT a collective call: the epilogue kernel of the step exchanges the five partials over NVLink
+ * peer memory itself (every rank owns a small slot array that the other ranks' epilogues write with peer stores; CUDA
+ * IPC maps the arrays across the processes) and adds them in rank order, so losses_out holds bitwise the same global
+ * sums on every rank when the step's kernels are done -- no extra launch, no library latency on the step.
+ *   every rank:  sfm_peer_create(nranks, rank, &peer, handle)   -> 64 opaque bytes (a cudaIpcMemHandle_t)
+ *   host side:   all-gather the handles of all ranks in rank order (nranks x 64 bytes)
+ *   every rank:  sfm_peer_connect(peer, all_handles); then a host barrier before the first step
+ *   every step:  sfm_loss_forward_backward_peer(desc, in, losses_out, grads, workspace, peer, stream)
+ *                (graph-capturable; every rank must run the same number of steps: step k of one rank waits, inside the
+ *                 epilogue kernel and for at most ~2 s, for step k of the others; on that timeout the losses are NaN)
+ *   at the end:  a host barrier, then sfm_peer_destroy(peer)
+ * One node, one process per GPU, up to 16 ranks, GPUs with peer access (NVLink / NVSwitch).                        */
+#define SFM_IPC_HANDLE_BYTES 64
+typedef struct SfmPeer SfmPeer;
+int sfm_peer_create(int nranks, int rank, SfmPeer** peer_out, void* ipc_handle_out);
+int sfm_peer_connect(SfmPeer* peer, const void* all_handles);
+int sfm_peer_destroy(SfmPeer* peer);
+int sfm_loss_forward_backward_peer(const SfmDesc* desc, const SfmInputs* in, float* losses_out, const SfmGrads* grads,
+                                   void* workspace, SfmPeer* peer, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,7 +159,7 @@ int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyr
 }
 
 int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const SfmGrads* grads, const float* gy,
-             const SfmDebug* dbg, void* workspace, cudaStream_t st) {
+             const SfmDebug* dbg, void* workspace, cudaStream_t st, const SfmPeerDev* peer = nullptr) {
   int rc = sfm_validate_desc(d);
   if (rc) return rc;
   const bool reuse = (d->flags & SFM_FLAG_REUSE_PYRAMID) != 0;
@@ -212,6 +212,8 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   p.acc = (double*)(ws + L.off_acc);
   p.counter = (unsigned*)(ws + L.off_counter);
   p.losses_out = losses_out;
+  p.peer = SfmPeerDev{};
+  if (peer) p.peer = *peer;
   p.gposes = grads ? grads->gposes : nullptr;
   p.smooth_reg = d->smooth_reg;
   p.exp_reg = m.use_exp ? d->exp_reg : 0.f;
@@ -260,6 +262,16 @@ extern "C" int sfm_loss_forward_backward(const SfmDesc* desc, const SfmInputs* i
   if (!losses_out) { sfm_set_error("losses_out is NULL"); return SFM_E_NULL_POINTER; }
   if (!grads) { sfm_set_error("grads is NULL"); return SFM_E_NULL_POINTER; }
   return run_loss(desc, in, losses_out, grads, nullptr, nullptr, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int sfm_loss_forward_backward_peer(const SfmDesc* desc, const SfmInputs* in, float* losses_out,
+                                              const SfmGrads* grads, void* workspace, SfmPeer* peer, void* stream) {
+  if (!losses_out) { sfm_set_error("losses_out is NULL"); return SFM_E_NULL_POINTER; }
+  if (!grads) { sfm_set_error("grads is NULL"); return SFM_E_NULL_POINTER; }
+  if (!peer) { sfm_set_error("peer is NULL"); return SFM_E_NULL_POINTER; }
+  const SfmPeerDev* dev = sfm_peer_dev(peer);
+  if (!dev) { sfm_set_error("sfm_loss_forward_backward_peer: the peer object is not connected (sfm_peer_connect)"); return SFM_E_UNSUPPORTED; }
+  return run_loss(desc, in, losses_out, grads, nullptr, nullptr, workspace, (cudaStream_t)stream, dev);
 }
 
 extern "C" int sfm_scale_grads(const SfmDesc* desc, const float* gy, const SfmGrads* grads, void* stream) {

@@ -1,5 +1,8 @@
 // comm.cu -- the one collective of the sharded path: the all-reduce of the five loss partials (SURVEY 8(e);
-// the reference analogue is Chainer's MultiprocessParallelUpdater reduce, config_utils.py:123-126).
+// the reference analogue is Chainer's MultiprocessParallelUpdater reduce, config_utils.py:123-126).  Two forms:
+//   SfmPeer  (bottom of this file) the sum is done INSIDE the epilogue kernel over NVLink peer memory (CUDA IPC mapped
+//            slot arrays, plain peer stores + flags; fused_loss.cu: epilogue_losses) -- no extra launch;
+//   SfmComm  an NCCL all-reduce enqueued behind the step (the library-call baseline).
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy the process already holds, e.g. the one bundled
 // with torch, or the one named with sfm_nccl_set_library) so that libsfmloss.so itself has no link-time NCCL
@@ -15,6 +18,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "kernels.h"
 
 namespace {
 
@@ -133,3 +137,81 @@ extern "C" int sfm_allreduce_partials(SfmComm* comm, float* losses, int count, v
   return nccl_check(g_nccl.AllReduce(losses, losses, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, comm->comm, (cudaStream_t)stream),
                     "ncclAllReduce");
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// SfmPeer: slot arrays for the in-kernel cross-GPU sum (one process per GPU, one node, NVLink / NVSwitch)
+// ------------------------------------------------------------------------------------------------
+struct SfmPeer {
+  int nranks, rank;
+  char* local;                       // [2][nranks] SfmPeerSlot + the step counter
+  void* mapped[SFM_MAX_PEERS];       // peers' arrays as mapped here (mapped[rank] == local)
+  bool connected;
+  SfmPeerDev dev;
+};
+
+static size_t peer_bytes(int nranks) { return sfm_align_up((size_t)2 * nranks * sizeof(SfmPeerSlot), 256) + 256; }
+
+extern "C" int sfm_peer_create(int nranks, int rank, SfmPeer** peer_out, void* ipc_handle_out) {
+  if (!peer_out || !ipc_handle_out) { sfm_set_error("sfm_peer_create: null pointer"); return SFM_E_NULL_POINTER; }
+  if (nranks < 1 || nranks > SFM_MAX_PEERS || rank < 0 || rank >= nranks) {
+    sfm_set_error("sfm_peer_create: rank %d outside a world of %d (1..%d ranks)", rank, nranks, SFM_MAX_PEERS);
+    return SFM_E_INVALID_DESC;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == SFM_IPC_HANDLE_BYTES, "SFM_IPC_HANDLE_BYTES");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { sfm_set_error("no CUDA device: libsfmloss has no CPU fallback"); return SFM_E_NO_DEVICE; }
+  SfmPeer* q = new (std::nothrow) SfmPeer();
+  if (!q) { sfm_set_error("out of host memory"); return SFM_E_INVALID_DESC; }
+  q->nranks = nranks; q->rank = rank; q->connected = false;
+  for (int r = 0; r < SFM_MAX_PEERS; ++r) q->mapped[r] = nullptr;
+  cudaError_t e = cudaMalloc((void**)&q->local, peer_bytes(nranks));          // plain cudaMalloc: exportable with CUDA IPC
+  if (e == cudaSuccess) e = cudaMemset(q->local, 0, peer_bytes(nranks));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, q->local);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    sfm_set_error("sfm_peer_create: %s", cudaGetErrorString(e));
+    if (q->local) cudaFree(q->local);
+    delete q;
+    return (int)e;
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *peer_out = q;
+  return 0;
+}
+
+extern "C" int sfm_peer_connect(SfmPeer* q, const void* all_handles) {
+  if (!q || !all_handles) { sfm_set_error("sfm_peer_connect: null pointer"); return SFM_E_NULL_POINTER; }
+  if (q->connected) { sfm_set_error("sfm_peer_connect: already connected"); return SFM_E_UNSUPPORTED; }
+  const char* hs = (const char*)all_handles;
+  for (int r = 0; r < q->nranks; ++r) {
+    if (r == q->rank) { q->mapped[r] = q->local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + (size_t)r * sizeof(h), sizeof(h));
+    const cudaError_t e = cudaIpcOpenMemHandle(&q->mapped[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      sfm_set_error("sfm_peer_connect: cudaIpcOpenMemHandle of rank %d failed: %s (the ranks must be processes on GPUs of one node "
+                    "with peer access)", r, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  q->dev.nranks = q->nranks;
+  q->dev.rank = q->rank;
+  q->dev.counter = (unsigned*)(q->local + sfm_align_up((size_t)2 * q->nranks * sizeof(SfmPeerSlot), 256));
+  for (int r = 0; r < SFM_MAX_PEERS; ++r) q->dev.slots[r] = (SfmPeerSlot*)q->mapped[r < q->nranks ? r : q->rank];
+  q->connected = true;
+  return 0;
+}
+
+extern "C" int sfm_peer_destroy(SfmPeer* q) {
+  if (!q) return 0;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < q->nranks; ++r)
+    if (r != q->rank && q->mapped[r]) cudaIpcCloseMemHandle(q->mapped[r]);
+  if (q->local) cudaFree(q->local);
+  delete q;
+  return 0;
+}
+
+const SfmPeerDev* sfm_peer_dev(const SfmPeer* q) { return (q && q->connected) ? &q->dev : nullptr; }

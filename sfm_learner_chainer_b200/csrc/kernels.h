@@ -55,6 +55,21 @@ int sfm_launch_eval_depth(int B, int h, int w, int Hg, int Wg, const float* pred
 int sfm_launch_disp_activation(long long n, const float* x, float* disp, float* dact, cudaStream_t stream);
 int sfm_launch_pose_reduce(int B, int S, int hw, const float* x, float* poses_out, cudaStream_t stream);
 
+// Cross-GPU sum of the five loss partials inside the epilogue kernel, over NVLink peer memory (comm.cu: SfmPeer).
+// Every rank owns a slot array [2 parities][nranks] that the OTHER ranks' epilogues write with plain peer stores;
+// slots[r] is rank r's array as mapped into this process (CUDA IPC).  `counter` (local) numbers the steps.
+constexpr int SFM_MAX_PEERS = 16;
+struct SfmPeerSlot {
+  float v[5];
+  unsigned pad0, pad1;
+  unsigned seq;          // step number the five values belong to (written last, after a system-scope fence)
+};
+struct SfmPeerDev {
+  int nranks, rank;      // nranks == 0: no cross-GPU sum
+  unsigned* counter;
+  SfmPeerSlot* slots[SFM_MAX_PEERS];
+};
+
 // Fused loss kernel parameters (one launch covers every scale, source and snippet).
 struct SfmFusedParams {
   int B, S, ns;
@@ -83,6 +98,7 @@ struct SfmFusedParams {
   double* acc;              // [4 + B*S*12]
   const float* sm_part;     // loss partials of the smoothness CTAs of the prologue kernel
   int n_sm_part;
+  SfmPeerDev peer;          // nranks > 0: losses_out receives the sums over all ranks (epilogue kernel)
   unsigned* counter;
   float* losses_out;        // [5] or nullptr
   float* gposes;            // [B][S][6] or nullptr
@@ -123,6 +139,9 @@ static inline cudaError_t sfm_launch_kernel(K kernel, unsigned grid, unsigned bl
   cfg.numAttrs = use ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+struct SfmPeer;
+const SfmPeerDev* sfm_peer_dev(const SfmPeer* q);      // comm.cu; nullptr until connected
 
 // mode bits for the launcher
 enum { SFM_MODE_EXP = 1, SFM_MODE_SSIM = 2, SFM_MODE_GRAD = 4, SFM_MODE_DEBUG = 8 };

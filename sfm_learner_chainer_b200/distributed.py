@@ -98,6 +98,57 @@ class LossPartialsComm(object):
             pass
 
 
+class PeerLossSum(object):
+    """The loss-partial sum done INSIDE the step's epilogue kernel over NVLink peer memory (include/sfmloss.h:
+    sfm_peer_* / sfm_loss_forward_backward_peer): no collective call, no extra launch.  One process per GPU on one
+    node.  `gather` is a callable bytes -> list of every rank's bytes in rank order (default: torch.distributed
+    all_gather_object); `barrier` a callable (default: torch.distributed.barrier).
+
+        peer = PeerLossSum(rank, world)                 # collective: every rank calls it, on its own device
+        losses, grads = op.forward_backward(..., peer=peer)    # losses = the GLOBAL sums, identical on every rank
+        peer.close()                                    # collective (barrier first: a peer may still be writing)
+    """
+
+    def __init__(self, rank, world_size, gather=None, barrier=None):
+        import ctypes as C
+        from . import lib as L
+        self._L, self._lib = L, L.load()
+        self.rank, self.world_size = int(rank), int(world_size)
+        self._barrier = barrier or self._torch_barrier
+        self._peer = C.c_void_p()
+        buf = (C.c_char * L.SFM_IPC_HANDLE_BYTES)()
+        L.check(self._lib.sfm_peer_create(self.world_size, self.rank, C.byref(self._peer), C.cast(buf, C.c_void_p)))
+        handles = (gather or self._torch_gather)(bytes(buf.raw))
+        if len(handles) != self.world_size or any(len(h) != L.SFM_IPC_HANDLE_BYTES for h in handles):
+            raise ValueError('gather() must return the %d-byte handle of every rank, in rank order' % L.SFM_IPC_HANDLE_BYTES)
+        allb = (C.c_char * (L.SFM_IPC_HANDLE_BYTES * self.world_size)).from_buffer_copy(b''.join(handles))
+        L.check(self._lib.sfm_peer_connect(self._peer, C.cast(allb, C.c_void_p)))
+        self._barrier()                                  # every rank has mapped every slot array before the first step
+
+    def _torch_gather(self, handle):
+        import torch.distributed as dist
+        if self.world_size == 1:
+            return [handle]
+        out = [None] * self.world_size
+        dist.all_gather_object(out, handle)
+        return out
+
+    def _torch_barrier(self):
+        import torch.distributed as dist
+        if self.world_size > 1 and dist.is_initialized():
+            dist.barrier()
+
+    @property
+    def handle(self):
+        return self._peer
+
+    def close(self):
+        if getattr(self, '_peer', None):
+            self._barrier()
+            self._lib.sfm_peer_destroy(self._peer)
+            self._peer = None
+
+
 class ShardedViewSynthesisLoss(object):
     """ViewSynthesisLoss over this rank's snippet shard; losses are completed by an allreduce.
 
@@ -106,9 +157,10 @@ class ShardedViewSynthesisLoss(object):
     the true global batch.  Every other ViewSynthesisLoss keyword (raw_disp_scales, raw_pose, edge_aware_smooth,
     n_scales) is forwarded."""
 
-    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None, comm=None, **kwargs):
+    def __init__(self, smooth_reg=0.0, exp_reg=0.0, ssim_rate=0.0, B_global=None, group=None, comm=None, peer=None, **kwargs):
         from .functions import ViewSynthesisLoss
         self.group = group
+        self.peer = peer                            # PeerLossSum: the sum happens inside the epilogue kernel (no collective call)
         self.comm = comm                            # LossPartialsComm: the all-reduce then runs through the C ABI, on the loss call's stream
         self.op = ViewSynthesisLoss(smooth_reg, exp_reg, ssim_rate, B_global=B_global, **kwargs)
         self._explicit = B_global is not None
@@ -137,6 +189,9 @@ class ShardedViewSynthesisLoss(object):
 
     def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, async_op=False, **kwargs):
         self._resolve_global_batch(src)
+        if self.peer is not None:
+            losses, grads = self.op.forward_backward(tgt, src, intrinsics, disps, poses, logits, peer=self.peer, **kwargs)
+            return losses, grads, None
         losses, grads = self.op.forward_backward(tgt, src, intrinsics, disps, poses, logits, **kwargs)
         if self.comm is not None:
             self.comm.allreduce(losses)

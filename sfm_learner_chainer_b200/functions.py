@@ -166,18 +166,26 @@ class ViewSynthesisLoss(object):
                                       C.c_void_p(D.current_stream(tgt))))
         self._ev_pyramid = D.record_event(tgt)
 
-    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, proj=None, kinv=None, reuse_pyramid=False):
+    def forward_backward(self, tgt, src, intrinsics, disps, poses, logits=None, proj=None, kinv=None, reuse_pyramid=False,
+                         peer=None):
         """Single fused pass: -> (losses (5,), dict(gdisps, gposes, glogits)) for upstream gradient 1.
-        reuse_pyramid: the workspace already holds this batch's pyramid (build_pyramid)."""
+        reuse_pyramid: the workspace already holds this batch's pyramid (build_pyramid).
+        peer: a distributed.PeerLossSum -- the batch is sharded by snippet over several GPUs (B_global set) and the
+        epilogue kernel completes the five losses across the ranks over NVLink peer memory."""
         desc, inp = self._pack(tgt, src, intrinsics, disps, poses, logits, proj, kinv)
         if reuse_pyramid:
             desc.flags |= L.SFM_FLAG_REUSE_PYRAMID
             D.wait_event(tgt, self._ev_pyramid)     # build_pyramid may have run on another stream
         g, out = self._alloc_grads(desc, tgt)
         losses = D.empty(tgt, (5,))
-        L.check(self._lib.sfm_loss_forward_backward(C.byref(desc), C.byref(inp), _vp(losses), C.byref(g),
-                                                    self._workspace(desc, tgt),
-                                                    C.c_void_p(D.current_stream(tgt))))
+        if peer is not None:
+            L.check(self._lib.sfm_loss_forward_backward_peer(C.byref(desc), C.byref(inp), _vp(losses), C.byref(g),
+                                                             self._workspace(desc, tgt), peer.handle,
+                                                             C.c_void_p(D.current_stream(tgt))))
+        else:
+            L.check(self._lib.sfm_loss_forward_backward(C.byref(desc), C.byref(inp), _vp(losses), C.byref(g),
+                                                        self._workspace(desc, tgt),
+                                                        C.c_void_p(D.current_stream(tgt))))
         if self._ev_pyramid is not None:
             self._ev_loss = D.record_event(tgt)
         return losses, out

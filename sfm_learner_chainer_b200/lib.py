@@ -20,6 +20,7 @@ SFM_E_UNSUPPORTED = -4
 SFM_E_NO_DEVICE = -5
 SFM_E_COMM = -6
 SFM_NCCL_UNIQUE_ID_BYTES = 128
+SFM_IPC_HANDLE_BYTES = 64
 
 LOSS_KEYS = ('total_loss', 'pixel_loss', 'smooth_loss', 'exp_loss', 'ssim_loss')   # base_model.py:119-123
 
@@ -89,6 +90,10 @@ SYMBOLS = {
     'sfm_comm_create': (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     'sfm_comm_destroy': (_i, [_vp]),
     'sfm_allreduce_partials': (_i, [_vp, _vp, _i, _vp]),
+    'sfm_peer_create': (_i, [_i, _i, C.POINTER(_vp), _vp]),
+    'sfm_peer_connect': (_i, [_vp, _vp]),
+    'sfm_peer_destroy': (_i, [_vp]),
+    'sfm_loss_forward_backward_peer': (_i, [_D, _I, _vp, _G, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -52,6 +52,25 @@ def _worker(rank, world, port, out_dir, B):
         graph.replay()
     torch.cuda.synchronize()
     l3_host = l3.cpu().numpy()
+    # ... and with NO collective call: the epilogue kernel sums the partials over NVLink peer memory (sfm_peer_*)
+    from sfm_learner_chainer_b200.distributed import PeerLossSum
+    peer = PeerLossSum(rank, world)
+    op3 = ShardedViewSynthesisLoss(peer=peer, **FLAGS)
+    for _ in range(3):
+        l4, g4, _ = op3.forward_backward(*args)
+    torch.cuda.synchronize()
+    graph2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        op3.forward_backward(*args)
+        side.synchronize()
+        with torch.cuda.graph(graph2, stream=side, capture_error_mode='thread_local'):
+            l5, _, _ = op3.forward_backward(*args)
+    for _ in range(5):
+        graph2.replay()
+    torch.cuda.synchronize()
+    l4_host, l5_host, gd4 = l4.cpu().numpy(), l5.cpu().numpy(), g4['gdisps'][0].cpu().numpy()
+    del graph2
+    peer.close()
     # a graph that captured the all-reduce holds a reference on the NCCL communicator: destroy it before the communicator
     # (ncclCommDestroy waits for such references)
     del graph, g3
@@ -60,7 +79,8 @@ def _worker(rank, world, port, out_dir, B):
     lo, hi = shard_range(B, rank, world)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), losses=losses.cpu().numpy(), gposes=grads['gposes'].cpu().numpy(),
              gdisp0=grads['gdisps'][0].cpu().numpy(), lo=lo, hi=hi, losses_abi=l2.cpu().numpy(), losses_graph=l3_host,
-             gdisp0_abi=g2['gdisps'][0].cpu().numpy(), B_global=op2.op.B_global)
+             gdisp0_abi=g2['gdisps'][0].cpu().numpy(), B_global=op2.op.B_global, losses_peer=l4_host, losses_peer_graph=l5_host,
+             gdisp0_peer=gd4)
     comm.close()
     dist.destroy_process_group()
 
@@ -96,3 +116,9 @@ def test_sharded_result_equals_single_gpu_result(tmp_path):
         np.testing.assert_allclose(z['losses_abi'][:5], host(lf)[:5], rtol=2e-6)         # C-ABI communicator, direct call
         np.testing.assert_allclose(z['losses_graph'][:5], host(lf)[:5], rtol=2e-6)       # ... and replayed inside a CUDA graph
         np.testing.assert_array_equal(z['gdisp0_abi'], host(gf['gdisps'][0])[sl])
+        np.testing.assert_allclose(z['losses_peer'][:5], host(lf)[:5], rtol=2e-6)        # summed inside the epilogue kernel (peer memory)
+        np.testing.assert_allclose(z['losses_peer_graph'][:5], host(lf)[:5], rtol=2e-6)
+        np.testing.assert_array_equal(z['gdisp0_peer'], host(gf['gdisps'][0])[sl])
+    # the in-kernel sum adds in rank order on every rank: bitwise identical results across the ranks
+    z0, z1 = np.load(tmp_path / 'rank0.npz'), np.load(tmp_path / 'rank1.npz')
+    np.testing.assert_array_equal(z0['losses_peer'], z1['losses_peer'])

@@ -648,3 +648,34 @@ def test_abi_communicator_world_of_one_inside_a_cuda_graph():
     torch.cuda.synchronize()
     np.testing.assert_array_equal(host(l2), host(ref))
     comm.close()
+
+
+def test_peer_loss_sum_world_of_one_inside_a_cuda_graph():
+    """sfm_peer_* / sfm_loss_forward_backward_peer on one GPU: the epilogue's in-kernel exchange with a world of one
+    returns the local losses, step after step (the device-side step counter) and when replayed as a CUDA graph."""
+    import torch
+    from sfm_learner_chainer_b200.distributed import PeerLossSum
+    flags = FLAGSETS['v1_ssim']
+    d = make_snippets(2, 2, 64, 208, seed=92)
+    g = dev_inputs(d)
+    args = (g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+    ref, gref = _op(flags).forward_backward(*args)
+    peer = PeerLossSum(0, 1)
+    op = _op(flags)
+    for _ in range(3):
+        l1, g1 = op.forward_backward(*args, peer=peer)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(host(l1), host(ref))
+        np.testing.assert_array_equal(host(g1['gposes']), host(gref['gposes']))
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        op.forward_backward(*args, peer=peer)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            l2, _ = op.forward_backward(*args, peer=peer)
+    for _ in range(4):
+        graph.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(l2), host(ref))
+    peer.close()
