@@ -357,8 +357,20 @@ def run_e2e(cfg_name, device, n_ctx=3, u8=False, min_steps=200, min_seconds=0.5,
         d = dict(tgt=rep(d['tgt']), src=rep(d['src']), intrinsics=rep(d['intrinsics']), disps=[rep(x) for x in d['disps']],
                  poses=rep(d['poses']), logits=[rep(x) for x in d['logits']])
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+    def pin_group(arrs):
+        """The arrays of one kind (four scales) as views of ONE pinned buffer, scale s+1 right behind scale s: the
+        library then moves them in a single copy (every copy has a fixed cost of several microseconds)."""
+        buf = torch.empty(sum(a.size for a in arrs), dtype=torch.float32).pin_memory()
+        out, off = [], 0
+        for a in arrs:
+            v = buf[off:off + a.size].view(*a.shape)
+            v.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            out.append(v)
+            off += a.size
+        return out
     hin = dict(tgt=pin(d['tgt']), src=pin(d['src']), K=pin(d['intrinsics']), poses=pin(d['poses']),
-               disps=[pin(x) for x in d['disps']], logits=[pin(x) for x in d['logits']])
+               disps=pin_group(d['disps']), logits=pin_group(d['logits']))
     desc = L.SfmDesc(B, S, H, W, 4, 0, c['smooth_reg'], c['exp_reg'], c['ssim_rate'], 0)
     inp = L.SfmInputs()
     inp.tgt, inp.src, inp.intrinsics, inp.poses = hin['tgt'].data_ptr(), hin['src'].data_ptr(), hin['K'].data_ptr(), hin['poses'].data_ptr()
@@ -390,7 +402,7 @@ def run_e2e(cfg_name, device, n_ctx=3, u8=False, min_steps=200, min_seconds=0.5,
             ctx = C.c_void_p()
             L.check(lib.sfm_host_ctx_create(C.byref(desc), C.byref(ctx)))
             ctxs.append(ctx)
-            ho = dict(gdisps=[pin(np.empty_like(x)) for x in d['disps']], glogits=[pin(np.empty_like(x)) for x in d['logits']],
+            ho = dict(gdisps=pin_group([np.zeros_like(x) for x in d['disps']]), glogits=pin_group([np.zeros_like(x) for x in d['logits']]),
                       gposes=pin(np.empty_like(d['poses'])), losses=pin(np.zeros(8, np.float32)))
             g = L.SfmGrads()
             g.gposes = ho['gposes'].data_ptr()
@@ -788,18 +800,19 @@ def run_b200(args):
     del runner
     if world == 1:
         # ---- e2e through the host-buffer C-ABI entry point (primary: the uint8-frame data layer the reference really has)
-        e8 = run_e2e(args.config, device, n_ctx=3, u8=True)
-        ef = run_e2e(args.config, device, n_ctx=3)
+        e8 = run_e2e(args.config, device, n_ctx=4, u8=True)
+        ef = run_e2e(args.config, device, n_ctx=4)
         es = run_e2e(args.config, device, n_ctx=1, repeats=1)
         line['e2e'] = dict(value=e8['value'], unit=UNIT, h2d_bytes_per_step=e8['h2d'], d2h_bytes_per_step=e8['d2h'],
                            steps_per_repeat=e8['steps'], repeats=e8['repeats'], h2d_gbs=e8['h2d_gbs'],
-                           api='sfm_loss_step_host_u8_submit/_wait, three host contexts in rotation (pinned host buffers; every step: '
+                           api='sfm_loss_step_host_u8_submit/_wait, four host contexts in rotation (pinned host buffers, the four scales of a kind '
+                               'back to back so that they travel as one copy; every step: '
                                'H2D of the decoded uint8 frames, K, augmentation draws, disparities, poses; ingest + prologue + fused '
                                'fwd+bwd + epilogue; D2H of the five losses and every gradient).  Median of three repeats of '
                                '>= 200 steps and >= 0.5 s each',
                            float_images=dict(value=ef['value'], h2d_bytes_per_step=ef['h2d'], d2h_bytes_per_step=ef['d2h'],
                                              repeats=ef['repeats'], h2d_gbs=ef['h2d_gbs'],
-                                             api='sfm_loss_step_host_submit/_wait: float32 images in (4 bytes per sample), three contexts'),
+                                             api='sfm_loss_step_host_submit/_wait: float32 images in (4 bytes per sample), four contexts'),
                            synchronous=dict(value=es['value'], api='sfm_loss_step_host, one step at a time, float32 images'))
         # ---- other single-GPU BASELINE shapes, device timed
         if not args.no_other:
@@ -832,12 +845,12 @@ def run_b200(args):
         # e2e at N GPUs: every rank runs the host-buffer path on its shard; aggregate = total pixels / slowest rank
         trace('e2e')
         dist.barrier()
-        e8 = run_e2e(args.config, device, n_ctx=3, u8=True, repeats=3)
+        e8 = run_e2e(args.config, device, n_ctx=4, u8=True, repeats=3)
         t = torch.tensor([wl.pix / e8['value']], device=device)      # us per step on this rank (pix / Mpix/s)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         line['e2e'] = dict(value=total_pix / float(t.item()), unit=UNIT, h2d_bytes_per_step=e8['h2d'] * world,
                            d2h_bytes_per_step=e8['d2h'] * world, steps_per_repeat=e8['steps'],
-                           api='sfm_loss_step_host_u8_submit/_wait on every rank (its snippet shard, three host contexts); '
+                           api='sfm_loss_step_host_u8_submit/_wait on every rank (its snippet shard, four host contexts); '
                                'median of three repeats of >= 200 steps and >= 0.5 s; total pixels / slowest rank')
         del wl
         torch.cuda.empty_cache()

@@ -244,7 +244,9 @@ int sfm_loss_step_host(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, 
  * step k+1 while step k runs): _submit enqueues the H2D copies, the kernels and the D2H copies on the context's
  * own stream and returns; _wait blocks until they are done.  The host buffers of a submitted step must stay
  * valid (and, for the outputs, untouched) until _wait returns.  With two contexts used alternately the copies of
- * one step overlap the kernels of the other (pinned memory required for the overlap). */
+ * one step overlap the kernels of the other (pinned memory required for the overlap).  Host arrays of one kind (disps,
+ * logits, gdisps, glogits) that lie back to back in scale order are moved in ONE copy each (every copy has a fixed cost of
+ * several microseconds); separate arrays work the same, one copy per scale. */
 int sfm_loss_step_host_submit(SfmHostCtx* ctx, const SfmInputs* in, float* losses_out, const SfmGrads* grads);
 int sfm_loss_step_host_wait(SfmHostCtx* ctx);
 

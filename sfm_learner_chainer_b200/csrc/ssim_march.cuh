@@ -20,6 +20,27 @@ namespace {
 
 constexpr int SSIM_IW = 28;     // interior columns per strip
 
+// Three channels as one packed pair (channels 0, 1: FFMA2 / FADD2 / FMUL2 of sm_100, one issue slot for two
+// lanes) plus a scalar (channel 2).  Used for the SSIM statistics and gradient fields (tolerance-checked region; the
+// individually rounded coordinate chain and the blend stay scalar).  The packed forms have the same FP32 throughput
+// as scalar code; what they save is issue slots, which is what bounds this kernel.
+struct V3 {
+  float2 a;
+  float b;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.a = make_float2(x, y); r.b = z; return r; }
+__device__ __forceinline__ V3 v3s(float s) { return v3(s, s, s); }
+__device__ __forceinline__ V3 operator+(const V3& x, const V3& y) { V3 r; r.a = __fadd2_rn(x.a, y.a); r.b = x.b + y.b; return r; }
+__device__ __forceinline__ V3 operator*(const V3& x, const V3& y) { V3 r; r.a = __fmul2_rn(x.a, y.a); r.b = x.b * y.b; return r; }
+__device__ __forceinline__ V3 vfma(const V3& x, const V3& y, const V3& z) { V3 r; r.a = __ffma2_rn(x.a, y.a, z.a); r.b = fmaf(x.b, y.b, z.b); return r; }
+__device__ __forceinline__ V3 vneg(const V3& x) { return v3(-x.a.x, -x.a.y, -x.b); }
+__device__ __forceinline__ V3 vshfl_up(const V3& x) {
+  return v3(__shfl_up_sync(0xffffffffu, x.a.x, 1), __shfl_up_sync(0xffffffffu, x.a.y, 1), __shfl_up_sync(0xffffffffu, x.b, 1));
+}
+__device__ __forceinline__ V3 vshfl_down(const V3& x) {
+  return v3(__shfl_down_sync(0xffffffffu, x.a.x, 1), __shfl_down_sync(0xffffffffu, x.a.y, 1), __shfl_down_sync(0xffffffffu, x.b, 1));
+}
+
 struct StripTask {
   int s, b, x0, y0, y1;
 };
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
     }
     __syncwarp();
     // rings: window row sums (P, P^2, P.T, T, T^2 per channel), gradient-field row sums, forward records
-    float hs[3][15], gs[3][9];
+    V3 hs[3][5], gs[3][3];        // [ring slot][field]: (P, P^2, P.T, T, T^2) and (g_a, g_s, g_c) row sums, three channels each
     Rec rec[3];
     bool mask[3];                                        // all-zero mask of the row's pixel (base_model.py:96)
     float dq[3];                                         // disparity / target rows fetched ahead
@@ -147,9 +168,9 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
-      for (int q = 0; q < 15; ++q) hs[k][q] = 0.f;
+      for (int q = 0; q < 5; ++q) hs[k][q] = v3s(0.f);
 #pragma unroll
-      for (int q = 0; q < 9; ++q) gs[k][q] = 0.f;
+      for (int q = 0; q < 3; ++q) gs[k][q] = v3s(0.f);
       mask[k] = true;
 #pragma unroll
       for (int c = 0; c < 3; ++c) rec[k].Ix[c] = rec[k].Iy[c] = rec[k].P[c] = rec[k].T[c] = 0.f;
@@ -279,73 +300,67 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
 #endif
       // ---------------- stage B: row sums of P, P^2, P.T, T, T^2 over lanes-1..+1 (zero outside the image)
       {
-        float* h0 = hs[cur];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float pv = rc_.P[c], tv = rc_.T[c];
-          const float pl = __shfl_up_sync(0xffffffffu, pv, 1), prr = __shfl_down_sync(0xffffffffu, pv, 1);
-          const float tl = __shfl_up_sync(0xffffffffu, tv, 1), tr = __shfl_down_sync(0xffffffffu, tv, 1);
-          h0[c * 5 + 0] = (pl + pv) + prr;
-          h0[c * 5 + 1] = fmaf(prr, prr, fmaf(pv, pv, pl * pl));
-          h0[c * 5 + 2] = fmaf(prr, tr, fmaf(pv, tv, pl * tl));
-          h0[c * 5 + 3] = (tl + tv) + tr;
-          h0[c * 5 + 4] = fmaf(tr, tr, fmaf(tv, tv, tl * tl));
-        }
+        const V3 pv = v3(rc_.P[0], rc_.P[1], rc_.P[2]), tv = v3(rc_.T[0], rc_.T[1], rc_.T[2]);
+        const V3 pl = vshfl_up(pv), prr = vshfl_down(pv), tl = vshfl_up(tv), tr = vshfl_down(tv);
+        V3* h0 = hs[cur];
+        h0[0] = (pl + pv) + prr;
+        h0[1] = vfma(prr, prr, vfma(pv, pv, pl * pl));
+        h0[2] = vfma(prr, tr, vfma(pv, tv, pl * tl));
+        h0[3] = (tl + tv) + tr;
+        h0[4] = vfma(tr, tr, vfma(tv, tv, tl * tl));
       }
       // ---------------- stage C: SSIM at (rc = r-1, lane) from rows r-2, r-1, r
       const int rc = r - 1;
-      float g0[9];
+      V3 g0[3];
       {
-        const float* h0 = hs[cur];
-        const float* h1 = hs[pv1];
-        const float* h2 = hs[pv2];
+        const V3* h0 = hs[cur];
+        const V3* h1 = hs[pv1];
+        const V3* h2 = hs[pv2];
         const bool c_in = col_in && (rc >= 0) && (rc < h) && (r >= r_begin + 2);
         const bool live_px = c_in && !mask[pv1];
         const bool own_c = col_own && (rc >= t.y0) && (rc < t.y1);
         const float lw = (live_px && own_c) ? 1.f : 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          // window sums: Sp = 9a, Spp = 9 A(P^2), Spt = 9 A(PT), St = 9 my, Stt = 9 A(T^2)
-          const float Sp = (h2[c * 5 + 0] + h1[c * 5 + 0]) + h0[c * 5 + 0];
-          const float Spp = (h2[c * 5 + 1] + h1[c * 5 + 1]) + h0[c * 5 + 1];
-          const float Spt = (h2[c * 5 + 2] + h1[c * 5 + 2]) + h0[c * 5 + 2];
-          const float St = (h2[c * 5 + 3] + h1[c * 5 + 3]) + h0[c * 5 + 3];
-          const float Stt = (h2[c * 5 + 4] + h1[c * 5 + 4]) + h0[c * 5 + 4];
-          // 81 x the reference's quantities: n1 = 2 a my + c1, n2 = 2 sxy + c2, d1 = a^2 + my^2 + c1, d2 = sx + sy + c2
-          const float pp = Sp * Sp, tt = St * St, pt = Sp * St;
-          const float n1 = fmaf(2.f, pt, C1);
-          const float n2 = fmaf(2.f, fmaf(9.f, Spt, -pt), C2);
-          const float d1v = (pp + tt) + C1;
-          const float d2v = (fmaf(9.f, Spp, -pp) + fmaf(9.f, Stt, -tt)) + C2;
-          const float n = n1 * n2, dd = d1v * d2v;
-          const float rd = rcp_approx(dd);
-          const float q = n * rd;                          // SSIM
-          const float raw = fmaf(-0.5f, q, 0.5f);
-          ssim_part = fmaf(__saturatef(raw), lw, ssim_part);
-          if (GRAD) {
-            // d raw / d(Sp, Spp, Spt) with n, d in the 81x units (SURVEY A.7 rescaled):
-            //   g_n = dL/dn = -0.5 w / d ; g_d = dL/dd = 0.5 w n / d^2
-            //   dn/dSp = 2 St (n2 - n1) ; dn/dSpt = 18 n1 ; dd/dSp = 2 Sp (d2 - d1) ; dd/dSpp = 9 d1
-            const bool live = live_px && (raw >= 0.f) && (raw <= 1.f);     // F.clip passes gradient inside [0, 1]
-            const float g_n = live ? (-0.5f * wssim) * rd : 0.f;
-            const float g_d = -g_n * q;
-            g0[c * 3 + 0] = fmaf(g_n * St, n2 - n1, (g_d * Sp) * (d2v - d1v));   // (dL/dSp) / 2
-            g0[c * 3 + 1] = g_d * d1v;                                            // (dL/dSpp) / 9
-            g0[c * 3 + 2] = g_n * n1;                                             // (dL/dSpt) / 18
-          }
+        // window sums: Sp = 9a, Spp = 9 A(P^2), Spt = 9 A(PT), St = 9 my, Stt = 9 A(T^2)
+        const V3 Sp = (h2[0] + h1[0]) + h0[0];
+        const V3 Spp = (h2[1] + h1[1]) + h0[1];
+        const V3 Spt = (h2[2] + h1[2]) + h0[2];
+        const V3 St = (h2[3] + h1[3]) + h0[3];
+        const V3 Stt = (h2[4] + h1[4]) + h0[4];
+        // 81 x the reference's quantities: n1 = 2 a my + c1, n2 = 2 sxy + c2, d1 = a^2 + my^2 + c1, d2 = sx + sy + c2
+        const V3 k2 = v3s(2.f), k9 = v3s(9.f), kC1 = v3s(C1), kC2 = v3s(C2);
+        const V3 pp = Sp * Sp, tt = St * St, pt = Sp * St;
+        const V3 n1 = vfma(k2, pt, kC1);
+        const V3 n2 = vfma(k2, vfma(k9, Spt, vneg(pt)), kC2);
+        const V3 d1v = (pp + tt) + kC1;
+        const V3 d2v = (vfma(k9, Spp, vneg(pp)) + vfma(k9, Stt, vneg(tt))) + kC2;
+        const V3 n = n1 * n2, dd = d1v * d2v;
+        const V3 rd = v3(rcp_approx(dd.a.x), rcp_approx(dd.a.y), rcp_approx(dd.b));
+        const V3 q = n * rd;                          // SSIM
+        const V3 raw = vfma(v3s(-0.5f), q, v3s(0.5f));
+        ssim_part = fmaf((__saturatef(raw.a.x) + __saturatef(raw.a.y)) + __saturatef(raw.b), lw, ssim_part);
+        if (GRAD) {
+          // d raw / d(Sp, Spp, Spt) with n, d in the 81x units (SURVEY A.7 rescaled):
+          //   g_n = dL/dn = -0.5 w / d ; g_d = dL/dd = 0.5 w n / d^2
+          //   dn/dSp = 2 St (n2 - n1) ; dn/dSpt = 18 n1 ; dd/dSp = 2 Sp (d2 - d1) ; dd/dSpp = 9 d1
+          // F.clip passes gradient inside [0, 1]
+          const float wl = live_px ? -0.5f * wssim : 0.f;
+          const V3 wv = v3((raw.a.x >= 0.f && raw.a.x <= 1.f) ? wl : 0.f, (raw.a.y >= 0.f && raw.a.y <= 1.f) ? wl : 0.f,
+                           (raw.b >= 0.f && raw.b <= 1.f) ? wl : 0.f);
+          const V3 g_n = wv * rd;
+          const V3 g_d = vneg(g_n) * q;
+          g0[0] = vfma(g_n * St, n2 + vneg(n1), (g_d * Sp) * (d2v + vneg(d1v)));   // (dL/dSp) / 2
+          g0[1] = g_d * d1v;                                                       // (dL/dSpp) / 9
+          g0[2] = g_n * n1;                                                        // (dL/dSpt) / 18
         }
       }
       if (GRAD) {
         // ---------------- stage D: row sums of the three gradient fields of row rc
-        float* gh0 = gs[cur];
+        V3* gh0 = gs[cur];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) {
-          const float gl = __shfl_up_sync(0xffffffffu, g0[q], 1), grt = __shfl_down_sync(0xffffffffu, g0[q], 1);
-          gh0[q] = (gl + g0[q]) + grt;
-        }
+        for (int q = 0; q < 3; ++q) gh0[q] = (vshfl_up(g0[q]) + g0[q]) + vshfl_down(g0[q]);
         // ---------------- stages E + F: dL/dP and the warp backward for pixel (rf = r-2, lane)
-        const float* g1 = gs[pv1];
-        const float* g2 = gs[pv2];
+        const V3* g1 = gs[pv1];
+        const V3* g2 = gs[pv2];
 #if SFM_SSIM_SREC
         Rec rb;
         {
@@ -365,16 +380,20 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
 #endif
         const bool mf = mask[pv2];
         float gP[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float Aa = (g2[c * 3 + 0] + g1[c * 3 + 0]) + gh0[c * 3 + 0];
-          const float As = (g2[c * 3 + 1] + g1[c * 3 + 1]) + gh0[c * 3 + 1];
-          const float Ac = (g2[c * 3 + 2] + g1[c * 3 + 2]) + gh0[c * 3 + 2];
+        {
+          const V3 Aa = (g2[0] + g1[0]) + gh0[0];
+          const V3 As = (g2[1] + g1[1]) + gh0[1];
+          const V3 Ac = (g2[2] + g1[2]) + gh0[2];
           // dL/dP = sum over the 3x3 windows containing the pixel of dL/dSp + 2P dL/dSpp + T dL/dSpt
           //       = 2 Aa + 18 P As + 18 T Ac
-          const float gsv = fmaf(18.f, fmaf(rb.T[c], Ac, rb.P[c] * As), 2.f * Aa);
-          const float gl1 = mf ? 0.f : sign_times(rb.P[c] - rb.T[c], wpix);
-          gP[c] = do_f ? gsv + gl1 : 0.f;
+          const V3 Pb = v3(rb.P[0], rb.P[1], rb.P[2]), Tb = v3(rb.T[0], rb.T[1], rb.T[2]);
+          const V3 gsv = vfma(v3s(18.f), vfma(Tb, Ac, Pb * As), v3s(2.f) * Aa);
+          const float gs3[3] = {gsv.a.x, gsv.a.y, gsv.b};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float gl1 = mf ? 0.f : sign_times(rb.P[c] - rb.T[c], wpix);
+            gP[c] = do_f ? gs3[c] + gl1 : 0.f;
+          }
         }
         // sampler + projection backward; out-of-view pixels have Ix = Iy = 0 and r = 0
         const float gu = gP[0] * rb.Ix[0] + gP[1] * rb.Ix[1] + gP[2] * rb.Ix[2];

@@ -43,5 +43,14 @@ disp_activation(dev(rs.standard_normal(1000).astype(np.float32)), want_dact=True
 pose_reduce(dev(rs.standard_normal((2, 12, 2, 5)).astype(np.float32)), 2)
 gt = dev(rs.uniform(1, 60, (2, 47, 155)).astype(np.float32))
 evaluate_depth_batch(dev(rs.uniform(1, 20, (2, 1, 16, 52)).astype(np.float32)), gt, (gt > 20).to(torch.uint8), 1e-3, 80.0)
+# the in-kernel cross-GPU sum with a world of one (peer stores into the rank's own slot array)
+from sfm_learner_chainer_b200.distributed import PeerLossSum
+peer = PeerLossSum(0, 1)
+d = make_snippets(2, 2, 40, 72, seed=2)
+op = ViewSynthesisLoss(0.1, 0.0, 0.15)
+for _ in range(2):
+    op.forward_backward(dev(d['tgt']), dev(d['src']), dev(d['intrinsics']), [dev(x) for x in d['disps']], dev(d['poses']), None, peer=peer)
+torch.cuda.synchronize()
+peer.close()
 torch.cuda.synchronize()
 print('sanitize_case: done')
