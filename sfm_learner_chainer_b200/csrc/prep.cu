@@ -64,6 +64,16 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
         for (int k = 0; k < 6; ++k) pose[k] = p.poses[((size_t)b * p.S + i) * 6 + k];
       }
       sfm_build_proj(pose, K, P);
+      // A non-finite pose or intrinsic would make every pixel of this (snippet, source) pair project to NaN: out of view
+      // by the strict test of transform.py:128-131, but with NaN in the backward's 0 * P products.  Such a pair gets a
+      // finite projection that sends every pixel out of view instead (q = (1e30, 1e30, 1)): losses and gradients of the
+      // pair are exactly 0 (documented deviation: the reference propagates NaN).
+      bool finite = true;
+      for (int k = 0; k < 12; ++k) finite = finite && (fabsf(P[k]) <= 3.0e38f);
+      if (!finite) {
+        for (int k = 0; k < 12; ++k) P[k] = 0.f;
+        P[3] = 1e30f; P[7] = 1e30f; P[11] = 1.f;
+      }
       for (int k = 0; k < 12; ++k) p.proj_out[(size_t)t * 12 + k] = P[k];
     } else if (t < n_proj + n_kinv) {
       const int j = t - n_proj;

@@ -695,7 +695,8 @@ def test_non_finite_poses_and_huge_depths_are_out_of_view():
     """Documented domain deviation (spec arithmetic): a NaN / Inf pose or a camera-space depth
     beyond ~1e37 makes the pixel OUT OF VIEW (warped value 0, masked, gradient 0) where the reference would propagate
     NaN into the loss.  Pinned here: a (snippet, source) pair with a NaN pose behaves exactly like a pair thrown out of
-    view by a huge sideways translation, and a single near-zero disparity leaves every output finite."""
+    view by a huge sideways translation, and a single near-zero (but normal, positive) disparity leaves every output
+    finite."""
     flags = FLAGSETS['v1_ssim']
     d = make_snippets(2, 2, 64, 208, seed=93)
     ref = {k: (v.copy() if hasattr(v, 'copy') else [x.copy() for x in v]) for k, v in d.items()}
@@ -718,8 +719,8 @@ def test_non_finite_poses_and_huge_depths_are_out_of_view():
     np.testing.assert_array_equal(out[1][2][0, 1], out[0][2][0, 1])            # the healthy pairs are untouched
     np.testing.assert_array_equal(out[1][2][1, 0], out[0][2][1, 0])
     assert not out[1][2][0, 0].any() and not out[1][2][1, 1].any()              # no gradient through a non-finite pose
-    # a disparity of 1e-38 (depth 1e38: the projection overflows) at one pixel
-    d['disps'][0][0, 0, 10, 20] = 1e-38
+    # a disparity of 2e-38 (the smallest normal floats; depth 5e37: the projection overflows) at one pixel
+    d['disps'][0][0, 0, 10, 20] = 2e-38
     g = dev_inputs(d)
     op = _op(flags)
     l, gr = op.forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])

@@ -89,8 +89,10 @@ def test_raw_mode_equals_stage_plus_plain_mode(flagset, mask):
     fused = _op(flags, raw_disp_scales=mask, raw_pose=True)
     l1, dbg1 = fused.forward(tgt, src, K, ins, xp, logits, debug=True)
     l1b, g1 = fused.forward_backward(tgt, src, K, ins, xp, logits)
-    np.testing.assert_array_equal(host(l1), host(l0))
-    np.testing.assert_array_equal(host(l1b), host(l0b))
+    # the five scalars are sums of per-task fp32 partials and the raw-input instances may run with another task shape
+    # (the source-split SSIM variant is plain-mode only): equal to summation order, i.e. a few ulp
+    np.testing.assert_allclose(host(l1), host(l0), rtol=5e-7, atol=0)
+    np.testing.assert_allclose(host(l1b), host(l0b), rtol=5e-7, atol=0)
     for s in range(4):
         for k in ('u0', 'v0', 'inb', 'P'):
             np.testing.assert_array_equal(host(dbg1[k][s]), host(dbg0[k][s]), err_msg='%s scale %d' % (k, s))
