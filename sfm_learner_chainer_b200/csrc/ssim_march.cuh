@@ -78,19 +78,25 @@ struct IC { static constexpr int value = N; };
 #ifndef SFM_SSIM_FENCE
 #define SFM_SSIM_FENCE 1      // basic-block fence after the refill (see step)
 #endif
-#ifndef SFM_SSIM_SREC
-#define SFM_SSIM_SREC 1       // forward records in shared memory instead of registers
-#endif
 #ifndef SFM_MINB_SSIM
-#define SFM_MINB_SSIM 12
+#define SFM_MINB_SSIM 12      // resident warps per SM of the instances that keep the forward records in shared memory (168 registers)
+#endif
+#ifndef SFM_MINB_SSIM_REG
+#define SFM_MINB_SSIM_REG 8   // ... of the instances that keep them in registers (250 registers)
 #endif
 // NW = warps per CTA.  NW == 1: one warp walks the strip segment once per source.  NW == 2 (two sources, small
 // batches): the two warps of a CTA walk the same segment at the same time, one source each, so a task is half as
 // long and -- for the same number of resident warps -- twice as tall (half the halo rows).  gdisp stays
 // deterministic: warp 1 hands its per-row term to warp 0 through shared memory (one CTA barrier per row) and warp 0
 // applies both in the order of the sequential loop, with the same fused multiply-adds.
-template <bool GRAD, bool ACCUM, bool DEBUG, bool RAW, int NW>
-__global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
+// SREC: where the two-row delay line of forward records lives.  true: shared memory (34 LDS/STS wavefronts per row,
+// 168 registers, 3 warps per scheduler) -- the throughput form for grids of several waves.  false: registers (250
+// registers, 2 warps per scheduler, 6 % fewer instructions and a third fewer L1 data-pipe wavefronts) -- faster whenever
+// the whole grid is resident at once anyway (cfg2: 29.3 -> 26.6 us), slower when occupancy counts (cfg5: 933 -> 952 us).
+template <bool GRAD, bool ACCUM, bool DEBUG, bool RAW, int NW, bool SREC = true>
+__global__ void __launch_bounds__(32 * NW, (SREC ? SFM_MINB_SSIM : SFM_MINB_SSIM_REG) / NW)
+sfm_ssim_march_kernel(const __grid_constant__ SfmFusedParams p) {
+  constexpr bool SFM_SSIM_SREC = SREC;
   __shared__ float4 sP_all[NW][3];
   __shared__ float sG[(NW > 1) ? 3 * 2 * 32 : 1];       // [ring slot][gdd | dsc][lane] of warp 1's row term
   const int wi = (NW > 1) ? (int)(threadIdx.x >> 5) : 0;
@@ -361,9 +367,8 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
         // ---------------- stages E + F: dL/dP and the warp backward for pixel (rf = r-2, lane)
         const V3* g1 = gs[pv1];
         const V3* g2 = gs[pv2];
-#if SFM_SSIM_SREC
-        Rec rb;
-        {
+        Rec rb = rec[pv2];
+        if (SFM_SSIM_SREC) {
           const float* o = myrec + pv2 * 18 * 32;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -375,9 +380,6 @@ __global__ void __launch_bounds__(32 * NW, SFM_MINB_SSIM / NW) sfm_ssim_march_ke
           rb.q0 = o[12 * 32]; rb.q1 = o[13 * 32]; rb.q2 = o[14 * 32]; rb.r = o[15 * 32]; rb.depth = o[16 * 32];
           rb.dsc = RAW ? o[17 * 32] : rb.depth;
         }
-#else
-        const Rec& rb = rec[pv2];
-#endif
         const bool mf = mask[pv2];
         float gP[3];
         {
@@ -477,31 +479,43 @@ static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug,
   // (fewer halo rows); the per-row CTA barrier is charged 5 %.
   (void)want_warps;
   int hseg = 64, nw = 1;
+  bool srec = true;       // forward records in shared memory; false: the register-record instances (plain GRAD mode only)
   {
     const long long sched = (long long)g_num_sms * 4, slots = (long long)g_num_sms * SFM_MINB_SSIM;
+    const long long slots_reg = (long long)g_num_sms * SFM_MINB_SSIM_REG;
     const bool may_split = grad && !debug && p.raw_disp_mask == 0 && p.S == 2 && !getenv("SFM_SSIM_NOSPLIT");
+    const bool may_reg = grad && !debug && p.raw_disp_mask == 0;
     double best = 1e300;
-    for (int cand = 1; cand <= (may_split ? 2 : 1); ++cand)
-      for (int h = 8; h <= 64; ++h) {
-        long long n = 0;
-        for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + h - 1) / h);
-        const long long warps = n * cand;
-        const double rows = 3.0 * ((h + 4 + 2) / 3) * (cand == 1 ? p.S : 1) * (cand == 1 ? 1.0 : 1.05);
-        double cost;
-        if (warps > slots) {
-          cost = rows * 3.0 * (double)((warps + slots - 1) / slots);
-        } else {
-          const long long w = (warps + sched - 1) / sched;
-          cost = rows * (double)w / (w <= 1 ? 0.66 : w == 2 ? 0.9 : 1.0);
+    for (int var = 0; var <= (may_reg ? 1 : 0); ++var)
+      for (int cand = 1; cand <= (may_split ? 2 : 1); ++cand)
+        for (int h = 8; h <= 64; ++h) {
+          long long n = 0;
+          for (int s = 0; s < p.ns; ++s) n += (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW) * ((p.h[s] + h - 1) / h);
+          const long long warps = n * cand;
+          const double rows = 3.0 * ((h + 4 + 2) / 3) * (cand == 1 ? p.S : 1) * (cand == 1 ? 1.0 : 1.05);
+          double cost;
+          if (var == 1) {
+            // register-record instances: 2 warps per scheduler at most, 9 % faster per row; only while the whole grid is
+            // resident at once (above that the shared-memory instances' third warp per scheduler wins: measured at cfg5)
+            if (warps > slots_reg) continue;
+            const long long w = (warps + sched - 1) / sched;
+            cost = 0.91 * rows * (double)w / (w <= 1 ? 0.66 : 0.9);
+          } else if (warps > slots) {
+            cost = rows * 3.0 * (double)((warps + slots - 1) / slots);
+          } else {
+            const long long w = (warps + sched - 1) / sched;
+            cost = rows * (double)w / (w <= 1 ? 0.66 : w == 2 ? 0.9 : 1.0);
+          }
+          if (cost < best || (cost == best && cand == nw)) { best = cost; hseg = h; nw = cand; srec = (var == 0); }
         }
-        if (cost < best || (cost == best && cand == nw)) { best = cost; hseg = h; nw = cand; }
-      }
   }
   {
     const char* e = getenv("SFM_HSEG");          // development knobs
     if (e && atoi(e) > 0) hseg = atoi(e);
     const char* f = getenv("SFM_SSIM_NW");
     if (f && (atoi(f) == 1 || (atoi(f) == 2 && grad && !debug && p.raw_disp_mask == 0 && p.S == 2))) nw = atoi(f);
+    const char* g = getenv("SFM_SSIM_SREC");
+    if (g && (atoi(g) == 1 || (atoi(g) == 0 && grad && !debug && p.raw_disp_mask == 0))) srec = atoi(g) != 0;
   }
   p.hseg = hseg;
   int total = 0;
@@ -519,8 +533,18 @@ static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug,
   int rc;
   const bool raw = p.raw_disp_mask != 0;
   if (nw == 2) {
-    rc = accum ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false, false, 2>, p, stream, 2)
-               : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false, false, 2>, p, stream, 2);
+    if (srec)
+      rc = accum ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false, false, 2, true>, p, stream, 2)
+                 : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false, false, 2, true>, p, stream, 2);
+    else
+      rc = accum ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false, false, 2, false>, p, stream, 2)
+                 : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false, false, 2, false>, p, stream, 2);
+    if (rc) return rc;
+    return launch_epilogue(p, stream);
+  }
+  if (!srec) {
+    rc = accum ? launch_ssim_kernel(sfm_ssim_march_kernel<true, true, false, false, 1, false>, p, stream)
+               : launch_ssim_kernel(sfm_ssim_march_kernel<true, false, false, false, 1, false>, p, stream);
     if (rc) return rc;
     return launch_epilogue(p, stream);
   }

@@ -107,10 +107,11 @@ def test_loss_and_gradients_match_oracle(flagset, B, S, H, W, seed, harsh):
 
 # BASELINE.json configs[3] (sfm_learner_v1_odom.yml:14-16, 5-frame snippets, 128x416) and configs[4] (256x832, SSIM
 # flags of sfm_learner_v1_ssim.yml:14-17) at their own shapes, with the launch variant the full batches pick
-# (B = 32: 8 runs per L1 task; B = 64: 64-row strips, one warp per SSIM task) forced through the development knobs.
+# (B = 32: 8 runs per L1 task; B = 64: 64-row strips, one warp per SSIM task, forward records in shared memory) forced
+# through the development knobs.
 BIG_SHAPES = {
     'cfg4': dict(flagset='v1_odom', B=2, S=4, H=128, W=416, seed=70, env={'SFM_HSEG': '8'}),
-    'cfg5': dict(flagset='v1_ssim', B=1, S=2, H=256, W=832, seed=71, env={'SFM_HSEG': '64', 'SFM_SSIM_NW': '1'}),
+    'cfg5': dict(flagset='v1_ssim', B=1, S=2, H=256, W=832, seed=71, env={'SFM_HSEG': '64', 'SFM_SSIM_NW': '1', 'SFM_SSIM_SREC': '1'}),
 }
 
 
@@ -728,3 +729,23 @@ def test_non_finite_poses_and_huge_depths_are_out_of_view():
     assert all(np.isfinite(host(x)).all() for x in gr['gdisps'])
     _, dbg = op.forward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'], debug=True)
     assert not host(dbg['inb'][0])[0, :, 10, 20].any()
+
+
+def test_ssim_record_placements_agree(monkeypatch):
+    """The SSIM kernel keeps its two-row delay line of forward records in registers (sub-wave grids) or in shared memory
+    (large grids); the launch policy picks.  Same arithmetic in the same order: per-pixel gradients must be identical
+    bit for bit, for the one-warp and the source-split task shapes."""
+    flags = FLAGSETS['v1_ssim']
+    d = make_snippets(2, 2, 72, 136, seed=94, harsh=True)
+    g = dev_inputs(d)
+    for nw in ('1', '2'):
+        res = []
+        for srec in ('0', '1'):
+            monkeypatch.setenv('SFM_SSIM_NW', nw)
+            monkeypatch.setenv('SFM_SSIM_SREC', srec)
+            l, gr = _op(flags).forward_backward(g['tgt'], g['src'], g['intrinsics'], g['disps'], g['poses'], g['logits'])
+            res.append((host(l), [host(x) for x in gr['gdisps']], host(gr['gposes'])))
+        np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-6)
+        assert_grad_close(res[1][2], res[0][2], what='gposes')
+        for s in range(4):
+            np.testing.assert_array_equal(res[1][1][s], res[0][1][s], err_msg='gdisp scale %d, NW=%s' % (s, nw))
