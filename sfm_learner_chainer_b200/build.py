@@ -30,7 +30,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+    cmd = [_nvcc(), '--threads', '0', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-Xcompiler', '-fPIC', '-shared', '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
            '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl']
     cmd[1:1] = os.environ.get('SFM_NVCC_FLAGS', '').split()      # development knob, e.g. -DSFM_MINB=16

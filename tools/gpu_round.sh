@@ -7,6 +7,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 SMI=$!
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -2 gpurun_out/${tag}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/${tag}_bench_cfg2_driverflags.json 2> gpurun_out/${tag}_bench.err; echo "bench(driver flags) rc=$?"
 timeout 900 python bench.py > gpurun_out/${tag}_bench_cfg2.json 2>> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${tag}_bench_cfg2.json | cut -c1-600
