@@ -653,6 +653,9 @@ def strong_scaling_block(args, device, world, rank, comm, peer, peak):
         for mode in ('no_collective', 'loss_sum_in_epilogue_kernel_over_peer_memory', 'nccl_allreduce_inline', 'nccl_allreduce_overlapped',
                      'loss_sum_in_epilogue_kernel_plus_159MB_gradient_allreduce'):
             rmode = 'peer' if mode.startswith('loss_sum_in_epilogue') else ('inline' if mode == 'nccl_allreduce_inline' else 'overlap')
+            if rmode == 'peer' and peer is None:
+                res[mode] = dict(skipped='no peer access between the GPUs (CUDA IPC)')
+                continue
             cm = None if mode == 'no_collective' else (peer if rmode == 'peer' else comm)
             runner = StepRunner(wl, cm, rmode)
             how = {'inline': 'NCCL all-reduce of step k captured behind step k\'s epilogue (exposed)',
@@ -715,18 +718,42 @@ def run_b200(args):
         from sfm_learner_chainer_b200.distributed import LossPartialsComm
         comm = LossPartialsComm(rank, world)                 # the C ABI's NCCL communicator (sfm_comm_create): the library-call baseline
         from sfm_learner_chainer_b200.distributed import PeerLossSum
-        peer = PeerLossSum(rank, world)                      # slot arrays for the in-kernel sum over NVLink peer memory
+        # slot arrays for the in-kernel sum over NVLink peer memory (CUDA IPC).  Every rank must agree on whether it
+        # worked: without peer access between the GPUs the bench falls back to the NCCL all-reduce on all ranks.
+        peer_err = ''
+        try:
+            peer = PeerLossSum(rank, world, barrier=lambda: None)
+        except Exception as exc:                              # noqa: BLE001
+            peer, peer_err = None, str(exc)[:200]
+        flag = torch.tensor([1 if peer is not None else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and peer is not None:
+            peer._lib.sfm_peer_destroy(peer._peer)
+            peer._peer = None
+            peer = None
+        if peer is not None:
+            peer._barrier = lambda: dist.barrier()
+        dist.barrier()
     n_gpus = world
     peak, peak_src = measured_peak()
 
     c = CONFIGS[args.config]
     wl = Workload(args.config, device, B_global=c['B'] * world)
-    use_comm = peer if (world > 1 and not args.no_allreduce) else None
-    runner = StepRunner(wl, use_comm, 'peer')
-    collective_how = ('summed across the ranks inside every step\'s epilogue kernel over NVLink peer memory '
-                      '(sfm_loss_forward_backward_peer; no collective call, no extra launch)') if use_comm else None
+    use_comm = (peer if peer is not None else comm) if (world > 1 and not args.no_allreduce) else None
+    if world > 1:
+        dist.barrier()                                        # the ranks enter their first (peer-synchronised) steps together
+    if use_comm is not None and use_comm is peer:
+        runner = StepRunner(wl, use_comm, 'peer')
+        collective_how = ('summed across the ranks inside every step\'s epilogue kernel over NVLink peer memory '
+                          '(sfm_loss_forward_backward_peer; no collective call, no extra launch)')
+    else:
+        runner = StepRunner(wl, use_comm, 'overlap')
+        collective_how = ('all-reduced by sfm_allreduce_partials (NCCL), the call of step k-1 captured as a parallel branch of step '
+                          'k\'s graph (the in-kernel peer-memory sum is unavailable here: %s)' % peer_err) if use_comm else None
     if not args.no_graph:
         runner.capture()
+    elif use_comm is not None and use_comm is not peer:
+        runner = StepRunner(wl, use_comm, 'inline')
     trace('captured: %s' % collective_how)
     sampler = ClockSampler(local)
     sampler.start()

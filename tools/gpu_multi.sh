@@ -13,7 +13,7 @@ print('e2e', l['e2e']['value'])
 for name, ent in (l.get('strong_scaling') or {}).items():
     print(name, ent.get('single_gpu_us_per_step'))
     for k,v in ent.items():
-        if isinstance(v, dict): print('   ', k, round(v['us_per_step'],1), round(v['efficiency_vs_single_gpu'],3), v.get('reduced_equals_world_x_local'))
+        if isinstance(v, dict) and 'us_per_step' in v: print('   ', k, round(v['us_per_step'],1), round(v['efficiency_vs_single_gpu'],3), v.get('reduced_equals_world_x_local'))
 r=json.loads(open('gpurun_out/${tag}_bench_reference_${N}gpu.json').read().strip().splitlines()[-1])
 print('reference arm', r['value'], r['config'] == l['config'])
 PY
