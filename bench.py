@@ -448,15 +448,17 @@ def run_e2e(cfg_name, device, n_ctx=3, u8=False, min_steps=200, min_seconds=0.5,
                 repeats=[pix / t / 1e6 for t in secs])
 
 
+KERNEL_SOURCES = ('common.cuh', 'kernels.h', 'fused_loss.cu', 'ssim_march.cuh', 'prep.cu', 'smooth.cu', 'smooth_task.cuh')
+
+
 def csrc_sha():
-    """Short hash of the kernel sources: profiles/ncu_latest.json records the one it was captured with, so a stale
-    capture is not quoted as the traffic of the kernels that run now."""
+    """Short hash of the KERNEL sources (not the host-side api.cu / comm.cu): profiles/ncu_latest.json records the one it
+    was captured with, so a stale capture is not quoted as the traffic of the kernels that run now."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'sfm_learner_chainer_b200', 'csrc')
-    for f in sorted(os.listdir(d)):
-        if f.endswith(('.cu', '.cuh', '.h')):
-            h.update(open(os.path.join(d, f), 'rb').read())
+    for f in KERNEL_SOURCES:
+        h.update(open(os.path.join(d, f), 'rb').read())
     return h.hexdigest()[:16]
 
 
