@@ -509,6 +509,31 @@ static int sfm_launch_ssim(SfmFusedParams& p, bool grad, bool accum, bool debug,
           if (cost < best || (cost == best && cand == nw)) { best = cost; hseg = h; nw = cand; srec = (var == 0); }
         }
   }
+  if (srec && nw == 1) {
+    // Grids of many waves: the time follows the total number of row steps (measured at cfg5: 64 / 86 / 128 rows per
+    // segment -> 934 / 933 / 912 us for 276 / 276 / 270 row steps per strip), so a taller segment -- fewer halo rows --
+    // is taken when it saves at least 1.5 % of the row steps and still leaves three waves of tasks.
+    const long long slots = (long long)g_num_sms * SFM_MINB_SSIM;
+    auto work = [&](int h, long long* n_out) {
+      long long n = 0, wk = 0;
+      for (int s = 0; s < p.ns; ++s) {
+        const long long strips = (long long)p.B * ((p.w[s] + SSIM_IW - 1) / SSIM_IW);
+        const int full = p.h[s] / h, rem = p.h[s] - full * h;
+        n += strips * (full + (rem ? 1 : 0));
+        wk += strips * ((long long)full * (3 * ((h + 4 + 2) / 3)) + (rem ? 3 * ((rem + 4 + 2) / 3) : 0));
+      }
+      *n_out = n;
+      return wk;
+    };
+    long long n0 = 0;
+    long long w0 = work(hseg, &n0);
+    if (n0 > 3 * slots)
+      for (int h2 : {96, 128, 192, 256}) {
+        long long n2 = 0;
+        const long long w2 = work(h2, &n2);
+        if (n2 >= 3 * slots && (double)w2 < 0.985 * (double)w0) { hseg = h2; w0 = w2; }
+      }
+  }
   {
     const char* e = getenv("SFM_HSEG");          // development knobs
     if (e && atoi(e) > 0) hseg = atoi(e);

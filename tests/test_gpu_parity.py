@@ -107,11 +107,11 @@ def test_loss_and_gradients_match_oracle(flagset, B, S, H, W, seed, harsh):
 
 # BASELINE.json configs[3] (sfm_learner_v1_odom.yml:14-16, 5-frame snippets, 128x416) and configs[4] (256x832, SSIM
 # flags of sfm_learner_v1_ssim.yml:14-17) at their own shapes, with the launch variant the full batches pick
-# (B = 32: 8 runs per L1 task; B = 64: 64-row strips, one warp per SSIM task, forward records in shared memory) forced
+# (B = 32: 8 runs per L1 task; B = 64: 128-row strips, one warp per SSIM task, forward records in shared memory) forced
 # through the development knobs.
 BIG_SHAPES = {
     'cfg4': dict(flagset='v1_odom', B=2, S=4, H=128, W=416, seed=70, env={'SFM_HSEG': '8'}),
-    'cfg5': dict(flagset='v1_ssim', B=1, S=2, H=256, W=832, seed=71, env={'SFM_HSEG': '64', 'SFM_SSIM_NW': '1', 'SFM_SSIM_SREC': '1'}),
+    'cfg5': dict(flagset='v1_ssim', B=1, S=2, H=256, W=832, seed=71, env={'SFM_HSEG': '128', 'SFM_SSIM_NW': '1', 'SFM_SSIM_SREC': '1'}),
 }
 
 
