@@ -152,7 +152,6 @@ int run_prep(const SfmDesc* d, const SfmInputs* in, void* workspace, bool do_pyr
   p.kinv_out = (float*)(ws + L.off_kinv);
   p.acc = (double*)(ws + L.off_acc);
   p.n_acc = (int)L.acc_doubles;
-  p.counter = (unsigned*)(ws + L.off_counter);
   p.raw_pose_hw = d->raw_pose_hw;
   p.posevec_out = (float*)(ws + L.off_posevec);
   return sfm_launch_prep(p, sm, sm_mode, st);
@@ -210,7 +209,6 @@ int run_loss(const SfmDesc* d, const SfmInputs* in, float* losses_out, const Sfm
   p.raw_disp_mask = d->raw_disp_scales;
   p.gy = gy;
   p.acc = (double*)(ws + L.off_acc);
-  p.counter = (unsigned*)(ws + L.off_counter);
   p.losses_out = losses_out;
   p.peer = SfmPeerDev{};
   if (peer) p.peer = *peer;
@@ -309,7 +307,6 @@ extern "C" int sfm_pyramid(const SfmDesc* desc, const float* tgt, const float* s
   }
   p.acc = (double*)(ws + L.off_acc);
   p.n_acc = 0;
-  p.counter = nullptr;
   return sfm_launch_prep(p, nullptr, 0, (cudaStream_t)stream);
 }
 
@@ -343,7 +340,7 @@ extern "C" int sfm_build_tables(const SfmDesc* desc, const float* poses, const f
   p.do_pyramid = 0; p.build_tables = 1;
   p.intrinsics = intrinsics; p.poses = poses;
   p.proj_out = proj_out; p.kinv_out = kinv_out;
-  p.acc = nullptr; p.n_acc = 0; p.counter = nullptr;
+  p.acc = nullptr; p.n_acc = 0;
   p.raw_pose_hw = desc->raw_pose_hw; p.posevec_out = nullptr;
   return sfm_launch_prep(p, nullptr, 0, (cudaStream_t)stream);
 }

@@ -38,7 +38,6 @@ struct SfmWsLayout {
   size_t off_proj;                 // float  [B][S][ns][12]  3x4 projection K4.T
   size_t off_kinv;                 // float  [B][ns][9]
   size_t off_acc;                  // double [4 + B*S*ns*12] loss sums (pixel, smooth, exp, ssim) + dL/dP per scale
-  size_t off_counter;              // unsigned: spare
   size_t off_posevec;              // float  [B][S][6]   6-DoF vectors reduced from the raw `poseout` map (raw_pose_hw > 0)
   size_t off_smpart;               // float  [tasks / 8] loss partials of the smoothness CTAs of the prologue kernel
   size_t acc_doubles;
@@ -89,8 +88,7 @@ static inline void sfm_ws_layout(const SfmDesc* d, SfmWsLayout* L) {
   L->acc_doubles = 4 + (size_t)d->B * d->S * d->n_scales * 12;
   L->off_acc = off;
   off += L->acc_doubles * sizeof(double);
-  L->off_counter = off;
-  off = sfm_align_up(off + 8, 256);
+  off = sfm_align_up(off, 256);
   L->off_posevec = off;
   off = sfm_align_up(off + (size_t)d->B * d->S * 6 * sizeof(float), 256);
   L->off_smpart = off;

@@ -19,15 +19,12 @@ struct SfmPrepParams {
   float* kinv_out;
   double* acc;
   int n_acc;
-  unsigned* counter;
   int raw_pose_hw;   // > 0: `poses` is the raw poseout map (B, 6S, raw_pose_hw); the reduced vectors go to posevec_out
   float* posevec_out;
   // filled by the launcher
-  long long pix_begin[SFM_MAX_SCALES];
   int n_pyr_blocks, n_tail_blocks;
   int n_mix_region;  // the smoothness CTAs are spread evenly over the first n_mix_region blocks after the tail blocks
-  int vec0;          // scale 0 copied 4 pixels per thread
-  int band, split;   // full-resolution rows per pyramid CTA; warps sharing one row
+  int band;          // full-resolution rows per pyramid CTA
 };
 
 // Second-order smoothness tasks that ride in the prologue kernel (smooth_task.cuh): strips x row segments of every
@@ -95,11 +92,10 @@ struct SfmFusedParams {
   int raw_pose_hw;          // > 0: gposes has the raw map's shape (B, 6S, raw_pose_hw)
   unsigned raw_disp_mask;   // bit s: disp[s] is pre-activation, gdisp[s] the gradient w.r.t. it
   const float* gy;          // upstream gradient (device scalar) or nullptr
-  double* acc;              // [4 + B*S*12]
+  double* acc;              // [4 + B*S*ns*12]
   const float* sm_part;     // loss partials of the smoothness CTAs of the prologue kernel
   int n_sm_part;
   SfmPeerDev peer;          // nranks > 0: losses_out receives the sums over all ranks (epilogue kernel)
-  unsigned* counter;
   float* losses_out;        // [5] or nullptr
   float* gposes;            // [B][S][6] or nullptr
   // loss weights per scale (host-computed in fp64, global batch in the denominators)

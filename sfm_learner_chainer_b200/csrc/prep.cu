@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(kPrepThreads) sfm_prep_kernel(const __grid_con
     } else {
       const int j = t - n_proj - n_kinv;
       if (j < p.n_acc) p.acc[j] = 0.0;
-      if (j == p.n_acc && p.counter) *p.counter = 0u;
     }
     return;
   }
@@ -216,11 +215,11 @@ int sfm_launch_prep(const SfmPrepParams& p_in, const SfmSmoothParams* sm_in, int
     else
       while (p.band > 2 && (long long)p.B * (1 + p.S) * ((p.H + p.band - 1) / p.band) < 148 * 2) p.band >>= 1;
   }
-  p.split = 1;
   p.n_pyr_blocks = (p.do_pyramid && p.ns > 1) ? p.B * (1 + p.S) * ((p.H + p.band - 1) / p.band) : 0;
-  const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc + 1;
+  const long long n_tail = (p.build_tables ? (long long)p.B * p.S * p.ns + (long long)p.B * p.ns : 0) + p.n_acc;
   p.n_tail_blocks = (int)((n_tail + kPrepThreads - 1) / kPrepThreads);
   const unsigned grid = (unsigned)(p.n_tail_blocks + p.n_pyr_blocks + (sm_mode ? sm.n_ctas : 0));
+  if (grid == 0) return 0;                        // e.g. sfm_pyramid with a single scale: nothing to build
   {
     int pct = 75;
     const char* e = getenv("SFM_SM_FRAC");        // development knob: share of the grid over which the smoothness CTAs are spread

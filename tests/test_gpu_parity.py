@@ -598,7 +598,7 @@ def test_torch_autograd_bridge_and_model_surface():
     loss = model(g['tgt'], g['src'], g['intrinsics'], g['intrinsics'])
     (3.0 * loss).backward()
     assert sorted(reports) == sorted(O.LOSS_KEYS)
-    np.testing.assert_allclose(float(loss), L['total_loss'], rtol=1e-5)
+    np.testing.assert_allclose(float(loss.detach()), L['total_loss'], rtol=1e-5)
     np.testing.assert_allclose(float(reports['ssim_loss']), 0.0)
     assert_grad_close(host(torch.stack([p.grad for p in poses], 1)), 3.0 * G['gpose'], what='gpose via autograd')
     assert_grad_close(host(disps[2].grad), 3.0 * G['gdisp'][2], what='gdisp via autograd')
@@ -749,3 +749,23 @@ def test_ssim_record_placements_agree(monkeypatch):
         assert_grad_close(res[1][2], res[0][2], what='gposes')
         for s in range(4):
             np.testing.assert_array_equal(res[1][1][s], res[0][1][s], err_msg='gdisp scale %d, NW=%s' % (s, nw))
+
+
+@pytest.mark.parametrize('ns', [1, 2, 3])
+def test_fewer_scales_match_oracle(ns):
+    """SfmDesc.n_scales < 4 (the ABI allows 1..4): with one scale the prologue kernel has no pyramid to build at all
+    (scale 0 is read from the caller's tensors); losses and gradients against the oracle run with the same n_scales."""
+    from sfm_learner_chainer_b200 import ViewSynthesisLoss
+    flags = FLAGSETS['v1_ssim']
+    d = make_snippets(2, 2, 64, 208, seed=95)
+    K = np.ascontiguousarray(d['intrinsics'][:, :ns])
+    L, G, _ = O.sfm_loss(d['tgt'], d['src'], K, d['disps'][:ns], d['poses'], None, O.LossConfig(n_scales=ns, **flags))
+    op = ViewSynthesisLoss(n_scales=ns, **flags)
+    losses, grads = op.forward_backward(to_dev(d['tgt']), to_dev(d['src']), to_dev(K), [to_dev(x) for x in d['disps'][:ns]],
+                                        to_dev(d['poses']), None)
+    np.testing.assert_allclose(host(losses), O.losses_vec(L), rtol=1e-5, atol=1e-9)
+    assert_grad_close(host(grads['gposes']), G['gpose'], what='gpose')
+    for s in range(ns):
+        assert_grad_close(host(grads['gdisps'][s]), G['gdisp'][s], what='gdisp[%d]' % s)
+    tp, sp = op.pyramid(to_dev(d['tgt']), to_dev(d['src']))
+    assert len(tp) == ns and len(sp) == ns

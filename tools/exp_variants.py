@@ -20,7 +20,10 @@ for v in variants:
     for kv in v.split():
         KNOBS.add(kv.split('=')[0])
 for name in cfgs:
-    wl = bench.Workload(name, dev)
+    blocal = None
+    if ':' in name:                      # cfg5:8 = the cfg5 shape with 8 snippets on this GPU (a shard of the global batch)
+        name, blocal = name.split(':')[0], int(name.split(':')[1])
+    wl = bench.Workload(name, dev, B_global=bench.CONFIGS[name]['B'] if blocal else None, B_local=blocal)
     n = 100 if name != 'cfg5' else 20
     for v in variants:
         for k in KNOBS:
