@@ -202,6 +202,56 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+STEPS_PER_GRAPH = 4
+
+
+def capture_step_graphs(torch, side, nsets, launch, error_mode='global', allow_groups=True):
+    """-> (one graph per buffer set, G, graphs of G consecutive steps each or None).  A trainer captures the loss path
+    inside its own step graph, between the CNN forward and backward: there the path's three kernels follow their
+    neighbours at kernel-to-kernel latency.  Replaying ONE step per graph adds a graph-to-graph launch boundary
+    (~4.5 us on B200) to every step that the path does not have in place; graphs of G = STEPS_PER_GRAPH consecutive
+    steps (distinct buffer sets, nothing shared between the steps) pay it once per G steps.  Both figures are
+    reported (`timing.one_step_per_graph`)."""
+    singles = []
+    for k in range(nsets):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode=error_mode):
+            launch(k, torch.cuda.current_stream())
+        singles.append(g)
+    G = next((c for c in (STEPS_PER_GRAPH, 2) if nsets % c == 0), 1) if allow_groups else 1
+    if os.environ.get('SFM_BENCH_STEPS_PER_GRAPH'):
+        G = int(os.environ['SFM_BENCH_STEPS_PER_GRAPH'])
+        G = G if (G >= 1 and nsets % G == 0) else 1
+    groups = None
+    if G > 1:
+        groups = []
+        for k0 in range(0, nsets, G):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side, capture_error_mode=error_mode):
+                for k in range(k0, k0 + G):
+                    launch(k, torch.cuda.current_stream())
+            groups.append(g)
+    torch.cuda.synchronize()
+    return singles, G, groups
+
+
+def replay_timed_steps(runner, steps, first, per_step, one_step_per_graph):
+    """The K timed steps: graphs of G consecutive steps when K is a multiple of G (and nothing runs between the steps),
+    else one graph (or one direct call) per step.  Returns the steps per graph used."""
+    G = runner.group if runner.group_graphs else 1
+    if G > 1 and not one_step_per_graph and per_step is None and steps % G == 0:
+        g0 = (first + G - 1) // G
+        for j in range(steps // G):
+            runner.group_graphs[(g0 + j) % len(runner.group_graphs)].replay()
+        runner.last = first + steps - 1
+        return G
+    for k in range(steps):
+        runner.step(first + k)
+        if per_step:
+            per_step(first + k)
+    return 1
+
+
 class Workload(object):
     """Pre-packed C-ABI calls over `nsets` rotating buffer sets (inputs AND outputs), so that with a
     working set below the 126 MB L2 consecutive steps still touch HBM."""
@@ -259,7 +309,7 @@ class Workload(object):
             t['inp'], t['g'] = inp, g
             t['wsp'] = C.c_void_p((t['ws'].data_ptr() + 255) // 256 * 256)
             self.sets.append(t)
-        self.graphs = None
+        self.graphs, self.group, self.group_graphs = None, 1, None
 
     def launch(self, k, stream, peer=None):
         t = self.sets[k % self.nsets]
@@ -273,9 +323,9 @@ class Workload(object):
             self.L.check(rc)
 
     def capture(self):
-        """One CUDA graph per buffer set (prep + fused kernel nodes): replays cost one launch each."""
+        """One CUDA graph per buffer set (prologue + fused + epilogue kernel nodes), and graphs of STEPS_PER_GRAPH
+        consecutive steps (consecutive buffer sets) for the timed loops: see steps_per_graph()."""
         torch = self.torch
-        self.graphs = []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -283,12 +333,8 @@ class Workload(object):
                 self.launch(k, side.cuda_stream)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for k in range(self.nsets):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                self.launch(k, torch.cuda.current_stream().cuda_stream)
-            self.graphs.append(g)
-        torch.cuda.synchronize()
+        self.graphs, self.group, self.group_graphs = capture_step_graphs(
+            torch, side, self.nsets, lambda k, st: self.launch(k, st.cuda_stream))
 
     def step(self, k):
         if self.graphs is not None:
@@ -296,7 +342,7 @@ class Workload(object):
         else:
             self.launch(k, self.torch.cuda.current_stream().cuda_stream)
 
-    def time_steps(self, steps, warmup, per_step=None):
+    def time_steps(self, steps, warmup, per_step=None, one_step_per_graph=False):
         torch = self.torch
         for k in range(warmup):
             self.step(k)
@@ -306,10 +352,7 @@ class Workload(object):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for k in range(steps):
-            self.step(warmup + k)
-            if per_step:
-                per_step(warmup + k)
+        replay_timed_steps(self, steps, warmup, per_step, one_step_per_graph)
         e1.record()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -498,8 +541,9 @@ class StepRunner(object):
     def __init__(self, wl, comm=None, mode='inline'):
         self.wl, self.comm = wl, comm
         self.mode = mode if comm is not None else None
-        self.graphs = None
+        self.graphs, self.group, self.group_graphs = None, 1, None
         self.last = None
+        self.timed_steps_per_graph = 1
         if self.mode == 'overlap':
             torch = wl.torch
             self.side2 = torch.cuda.Stream()
@@ -537,15 +581,10 @@ class StepRunner(object):
                 self._launch(k, side)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graphs = []
-        for k in range(wl.nsets):
-            g = torch.cuda.CUDAGraph()
-            # thread-local capture mode: torch's NCCL watchdog thread may query events while this thread captures
-            with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
-                self._launch(k, torch.cuda.current_stream())
-            graphs.append(g)
-        torch.cuda.synchronize()
-        self.graphs = graphs
+        # thread-local capture mode: torch's NCCL watchdog thread may query events while this thread captures.  Steps that
+        # fork an NCCL branch keep one step per graph
+        self.graphs, self.group, self.group_graphs = capture_step_graphs(
+            torch, side, wl.nsets, lambda k, st: self._launch(k, st), 'thread_local', allow_groups=self.mode in (None, 'peer'))
 
     def step(self, k):
         if self.graphs is not None:
@@ -559,7 +598,7 @@ class StepRunner(object):
         if self.mode == 'overlap' and self.last is not None:
             self._allreduce(self.last, self.wl.torch.cuda.current_stream().cuda_stream)
 
-    def time(self, steps, warmup, per_step=None, before_stop=None):
+    def time(self, steps, warmup, per_step=None, before_stop=None, one_step_per_graph=False):
         """ms per step between two CUDA events on the launching stream (all of a step's kernels, and the captured
         all-reduce, are on it or joined into it); `before_stop` runs right before the stop event (e.g. waits for
         side-stream work)."""
@@ -573,10 +612,7 @@ class StepRunner(object):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for k in range(steps):
-            self.step(warmup + k)
-            if per_step:
-                per_step(warmup + k)
+        self.timed_steps_per_graph = replay_timed_steps(self, steps, warmup, per_step, one_step_per_graph)
         self.finish()
         if before_stop:
             before_stop()
@@ -765,6 +801,14 @@ def run_b200(args):
     ms, t0, t1 = runner.time(args.steps, args.warmup)
     torch.cuda.synchronize()
     trace('timed %.4f ms' % ms)
+    steps_per_graph = runner.timed_steps_per_graph
+    ms_single = ms
+    if steps_per_graph > 1:                                   # the same K steps replayed one step per graph, for comparison
+        if world > 1:
+            dist.barrier()
+        ms_single, _, _ = runner.time(args.steps, args.warmup, one_step_per_graph=True)
+        torch.cuda.synchronize()
+        ms_single = max_over_ranks(ms_single, device, world)
     allreduce_ok = runner.reduced_rows_ok(world) if use_comm is not None else None
     trace('check %s' % allreduce_ok)
     if world > 1:
@@ -793,9 +837,15 @@ def run_b200(args):
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 config=config_dict(args.config, world),
                 timing=dict(buffer_sets=wl.nsets, rotation_mb=wl.nsets * wl.A_strict / 1e6, l2_mb=wl.l2_bytes / 1e6,
-                            launch=('CUDA graph replay of the step\'s %d kernel nodes (prologue: pyramid + tables + smoothness tasks; '
-                                    'fused loss; epilogue; programmatic dependent launches between them)' % n_launch)
+                            launch=('CUDA graph replay, %d consecutive step(s) per graph (each step = %d kernel nodes: prologue = pyramid + '
+                                    'tables + smoothness tasks; fused loss; epilogue; programmatic dependent launches between them; '
+                                    'consecutive steps use distinct buffer sets and share nothing)' % (steps_per_graph, n_launch))
                             if not args.no_graph else 'direct C-ABI calls',
+                            steps_per_graph=steps_per_graph,
+                            one_step_per_graph=dict(ms_per_step=ms_single, value=wl.pix * world / (ms_single * 1e-3) / 1e6,
+                                                    note='the same K steps with a graph-to-graph launch boundary behind every step '
+                                                         '(the figure of the earlier rounds); inside a trainer\'s own step graph the '
+                                                         'path has kernel-to-kernel boundaries only'),
                             parallelism=('snippet-sharded x%d (weak scaling: %d snippets per GPU, B_global = %d), no data-path '
                                          'collective call; the five loss partials of EVERY step are %s' % (
                                              world, wl.B, wl.B * world, collective_how)) if world > 1 else 'single GPU',
@@ -853,9 +903,11 @@ def run_b200(args):
                     continue
                 w2 = Workload(name, device)
                 w2.capture()
-                oms, _, _ = w2.time_steps(50, 5)
+                oms, _, _ = w2.time_steps(48, 5)
+                oms1, _, _ = w2.time_steps(48, 5, one_step_per_graph=True)
                 km, _ = w2.time_fused_kernel(50)
                 others[name] = dict(workload=describe(name), ms_per_step=oms, value=w2.pix / (oms * 1e-3) / 1e6, unit=UNIT,
+                                    steps_per_graph=w2.group if 48 % w2.group == 0 else 1, ms_per_step_one_step_per_graph=oms1,
                                     step_frac_of_hbm_peak=w2.A_strict / (oms * 1e-3) / 1e9 / peak,
                                     fused_kernel_us=km * 1e3,
                                     fused_kernel_frac_of_hbm_peak=w2.A_strict / (km * 1e-3) / 1e9 / peak,
