@@ -62,3 +62,39 @@ def test_b200_arm_rejects_a_gpu_count_that_is_not_the_world_size():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--gpus', '2', '--steps', '3'], stdout=subprocess.PIPE,
                          stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode != 0 and 'torch.distributed.run' in (out.stderr + out.stdout)
+
+
+def test_timed_steps_are_exactly_K_with_grouped_graphs():
+    """bench.replay_timed_steps: K steps from graphs of G consecutive steps when K is a multiple of G and nothing
+    runs between the steps; one graph per step otherwise.  Either way every buffer set is visited in rotation."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Graph(object):
+        def __init__(self, log, sets):
+            self.log, self.sets = log, sets
+
+        def replay(self):
+            self.log.extend(self.sets)
+
+    class Runner(object):
+        def __init__(self, nsets, G):
+            self.log, self.nsets, self.group = [], nsets, G
+            self.group_graphs = [Graph(self.log, list(range(k, k + G))) for k in range(0, nsets, G)] if G > 1 else None
+
+        def step(self, k):
+            self.log.append(k % self.nsets)
+
+    r = Runner(28, 4)
+    assert bench.replay_timed_steps(r, 20, 3, None, False) == 4
+    assert len(r.log) == 20 and r.log == [(4 + k) % 28 for k in range(20)]      # starts at the first group boundary after the warm-up
+    r = Runner(28, 4)
+    assert bench.replay_timed_steps(r, 2000, 50, None, False) == 4
+    assert len(r.log) == 2000 and set(r.log) == set(range(28))
+    assert all(b == (a + 1) % 28 for a, b in zip(r.log, r.log[1:]))              # consecutive steps never share a buffer set
+    for args in ((21, 3, None, False), (20, 3, None, True), (20, 3, lambda k: None, False)):
+        r = Runner(28, 4)
+        assert bench.replay_timed_steps(r, *args) == 1
+        assert r.log == [(3 + k) % 28 for k in range(args[0])]
+    r = Runner(3, 1)
+    assert bench.replay_timed_steps(r, 20, 3, None, False) == 1 and len(r.log) == 20
