@@ -879,19 +879,19 @@ def run_b200(args):
     del runner
     if world == 1:
         # ---- e2e through the host-buffer C-ABI entry point (primary: the uint8-frame data layer the reference really has)
-        e8 = run_e2e(args.config, device, n_ctx=4, u8=True)
-        ef = run_e2e(args.config, device, n_ctx=4)
+        e8 = run_e2e(args.config, device, n_ctx=8, u8=True)
+        ef = run_e2e(args.config, device, n_ctx=8)
         es = run_e2e(args.config, device, n_ctx=1, repeats=1)
         line['e2e'] = dict(value=e8['value'], unit=UNIT, h2d_bytes_per_step=e8['h2d'], d2h_bytes_per_step=e8['d2h'],
                            steps_per_repeat=e8['steps'], repeats=e8['repeats'], h2d_gbs=e8['h2d_gbs'],
-                           api='sfm_loss_step_host_u8_submit/_wait, four host contexts in rotation (pinned host buffers, the four scales of a kind '
+                           api='sfm_loss_step_host_u8_submit/_wait, eight host contexts in rotation (pinned host buffers, the four scales of a kind '
                                'back to back so that they travel as one copy; every step: '
                                'H2D of the decoded uint8 frames, K, augmentation draws, disparities, poses; ingest + prologue + fused '
                                'fwd+bwd + epilogue; D2H of the five losses and every gradient).  Median of three repeats of '
                                '>= 200 steps and >= 0.5 s each',
                            float_images=dict(value=ef['value'], h2d_bytes_per_step=ef['h2d'], d2h_bytes_per_step=ef['d2h'],
                                              repeats=ef['repeats'], h2d_gbs=ef['h2d_gbs'],
-                                             api='sfm_loss_step_host_submit/_wait: float32 images in (4 bytes per sample), four contexts'),
+                                             api='sfm_loss_step_host_submit/_wait: float32 images in (4 bytes per sample), eight contexts'),
                            synchronous=dict(value=es['value'], api='sfm_loss_step_host, one step at a time, float32 images'))
         # ---- other single-GPU BASELINE shapes, device timed
         if not args.no_other:
@@ -926,12 +926,12 @@ def run_b200(args):
         # e2e at N GPUs: every rank runs the host-buffer path on its shard; aggregate = total pixels / slowest rank
         trace('e2e')
         dist.barrier()
-        e8 = run_e2e(args.config, device, n_ctx=4, u8=True, repeats=3)
+        e8 = run_e2e(args.config, device, n_ctx=8, u8=True, repeats=3)
         t = torch.tensor([wl.pix / e8['value']], device=device)      # us per step on this rank (pix / Mpix/s)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         line['e2e'] = dict(value=total_pix / float(t.item()), unit=UNIT, h2d_bytes_per_step=e8['h2d'] * world,
                            d2h_bytes_per_step=e8['d2h'] * world, steps_per_repeat=e8['steps'],
-                           api='sfm_loss_step_host_u8_submit/_wait on every rank (its snippet shard, four host contexts); '
+                           api='sfm_loss_step_host_u8_submit/_wait on every rank (its snippet shard, eight host contexts); '
                                'median of three repeats of >= 200 steps and >= 0.5 s; total pixels / slowest rank')
         del wl
         torch.cuda.empty_cache()
